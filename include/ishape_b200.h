@@ -1,0 +1,268 @@
+/*
+ * ishape_b200.h — C ABI of libishape_b200.so
+ *
+ * B200 (sm_100a) kernels for the drag-guided triplane-diffusion editing step of
+ * jinli99/iShapEditing.  The reference has no FFI of its own (it is pure
+ * Python/PyTorch); every entry point below replaces one PyTorch library call
+ * (or a fixed group of them) that the reference issues on its hot path, and the
+ * comment on each entry point cites the reference call site it replaces.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     it is named host_*; the caller owns every buffer, including workspaces;
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as
+ *     void*), nothing synchronises, nothing allocates -> CUDA-graph capturable;
+ *   - activations are NHWC (channels innermost); the "stream" tensors (block
+ *     outputs, gradients) are fp32, GEMM operands are bf16 ("bf16 mode",
+ *     tcgen05 tensor cores) or fp32 ("fp32 mode", FFMA);
+ *   - return 0 on success, negative isb_status otherwise; the message is
+ *     available through isb_last_error() (thread local);
+ *   - callable from any host thread; no thread-affine state.
+ */
+#ifndef ISHAPE_B200_H
+#define ISHAPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISB_ABI_VERSION 1
+
+typedef void* isb_stream_t; /* cudaStream_t */
+
+enum isb_dtype { ISB_F32 = 0, ISB_BF16 = 1 };
+
+enum isb_status {
+  ISB_OK = 0,
+  ISB_ERR_ARG = -1,         /* bad argument / unsupported shape */
+  ISB_ERR_CUDA = -2,        /* CUDA runtime/driver error */
+  ISB_ERR_WORKSPACE = -3,   /* workspace too small */
+  ISB_ERR_NOT_INIT = -4     /* isb_init() not called for this device */
+};
+
+/* ---- library ---------------------------------------------------------- */
+int isb_abi_version(void);
+/* Select device, resolve cuTensorMapEncodeTiled, raise kernel smem limits.
+ * Must be called once per process per device before any other call. */
+int isb_init(int device);
+const char* isb_last_error(void);
+
+/* ---- layout ----------------------------------------------------------- */
+/* NCHW fp32 -> NHWC (fp32|bf16), channels zero-padded to c_pad >= C.
+ * Replaces `h = x.type(self.dtype)` (unet.py:657) + cuDNN's internal layout. */
+int isb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C,
+                     int H, int W, int c_pad, isb_stream_t stream);
+/* NHWC (fp32|bf16) with c_stride channels per pixel -> NCHW fp32 (first C). */
+int isb_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int N, int C,
+                     int H, int W, int c_stride, isb_stream_t stream);
+/* fp32 -> bf16 elementwise cast (n elements, n % 8 == 0). */
+int isb_cast_f32_bf16(const float* src, void* dst, size_t n, isb_stream_t stream);
+
+/* ---- convolution / linear as implicit GEMM ---------------------------- */
+/* out[n,h,w,co] = (accumulate ? out : 0) + bias[co] + residual[n,h,w,co]
+ *               + sum_{kh,kw,ci} a[n,h+kh-p,w+kw-p,ci] * w[co][(kh*ks+kw)*Cin+ci]
+ *               + sum_{ci2}      a2[n,h,w,ci2]         * w[co][ks*ks*Cin+ci2]
+ * Replaces nn.Conv2d 3x3/1x1 and nn.Conv1d k=1 (unet.py:185,211,222,286,294,
+ * 482,615 via nn.py:21-31) and, with the transposed/flipped packing, their
+ * cuDNN backward-data (autograd of drag_utils.py:383).
+ * a_dtype == ISB_BF16 selects the TMA + tcgen05 kernel (fp32 accumulation in
+ * TMEM); a_dtype == ISB_F32 selects the FFMA kernel ("fp32 mode"). */
+typedef struct isb_conv_desc {
+  const void* a;         /* [N,H,W,Cin], a_dtype */
+  int a_dtype;
+  int N, H, W, Cin;      /* bf16: Cin % 64 == 0; fp32: Cin % 16 == 0 */
+  int ksize;             /* 1 or 3 (stride 1, zero pad ksize/2) */
+  const void* a2;        /* optional second 1x1 source [N,H,W,Cin2] or NULL */
+  int Cin2;
+  const void* w;         /* packed [Cout][ksize*ksize*Cin + Cin2], a_dtype */
+  const float* bias;     /* [Cout] or NULL */
+  const float* residual; /* fp32 [N,H,W,Cout] or NULL */
+  void* out;             /* [N,H,W,Cout] */
+  int out_dtype;
+  int Cout;              /* % 8 == 0 */
+  int accumulate;        /* fp32 out only */
+  /* tuning overrides for the tcgen05 kernel; 0 = heuristic */
+  int block_n;           /* 64,128,192,256 */
+  int split_k;
+  int stages;
+} isb_conv_desc;
+size_t isb_conv2d_workspace(const isb_conv_desc* d);
+int isb_conv2d(const isb_conv_desc* d, void* workspace, size_t workspace_bytes,
+               isb_stream_t stream);
+
+/* ---- GroupNorm (+FiLM) (+SiLU) (+2x resample) ------------------------- */
+/* Source tensor x is the channel concatenation of x1 [N,H,W,C1] and (optional)
+ * x2 [N,H,W,C2], both fp32 NHWC — this fuses `th.cat([h, hs.pop()], dim=1)`
+ * (unet.py:663) into the consumer.
+ *   z   = GN_32groups(x) * gamma + beta                (nn.py:16-18, fp32)
+ *   z   = z * (1 + scale[n,c]) + shift[n,c]            if film   (unet.py:248-252)
+ *   a   = silu ? z*sigmoid(z) : z                       (unet.py:184,208,614)
+ *   a   = avgpool2x2(a) | nearest_up2x(a)               resample 1 | 2 (unet.py:107,136)
+ * Outputs (each optional unless noted):
+ *   stats [N,groups,2] fp32 (mean,rstd)  — required, kept for the backward
+ *   y     activation in y_dtype at output resolution — required
+ *   raw   x itself (concatenated) cast to raw_dtype at input resolution (operand
+ *         of the 1x1 skip convolution, unet.py:222)
+ *   xres  x resampled like `a`, fp32 (the `x = self.x_upd(x)` branch, unet.py:240)
+ * film points at [N, film_stride] fp32 with scale at [0,C) and shift at [C,2C). */
+typedef struct isb_gn_desc {
+  const float* x1; int C1;
+  const float* x2; int C2;
+  int N, H, W;            /* input resolution */
+  int groups; float eps;
+  const float* gamma; const float* beta;   /* [C1+C2] */
+  const float* film; int film_stride;      /* NULL = no FiLM */
+  int silu;
+  int resample;           /* 0 none, 1 down (avgpool 2x2), 2 up (nearest 2x) */
+  float* stats;           /* [N,groups,2] */
+  void* y; int y_dtype;
+  void* raw; int raw_dtype;
+  float* xres;
+} isb_gn_desc;
+/* scratch: device buffer of isb_gn_scratch_bytes(N, groups) bytes, must be
+ * zero-initialised once by the caller and is left zeroed by each call. */
+size_t isb_gn_scratch_bytes(int N, int groups);
+int isb_gn_forward(const isb_gn_desc* d, void* scratch, isb_stream_t stream);
+
+/* Backward of the above w.r.t. x (input gradient only; the reference's weight
+ * gradients — drag_utils.py:383 computes them and never reads them — are not
+ * produced).
+ *   dy    [N,Ho,Wo,C] fp32: gradient w.r.t. `y` (output resolution)
+ *   gres  optional [N,H,W,C] fp32 at INPUT resolution if gres_at_input, else at
+ *         output resolution and pulled back through the resample (the identity
+ *         / x_upd skip path): added to dx
+ *   gx1/gx2 fp32 gradient of x1/x2, overwritten or accumulated (acc1/acc2)
+ *   gx1_lo/gx2_lo optional copies of the final gx in lo_dtype (operand of the
+ *         upstream dgrad GEMM)
+ */
+typedef struct isb_gn_bwd_desc {
+  isb_gn_desc f;          /* forward description (stats is an INPUT here; y/raw/xres unused) */
+  const float* dy;
+  const float* gres; int gres_at_input;
+  float* gx1; int acc1; void* gx1_lo;
+  float* gx2; int acc2; void* gx2_lo;
+  int lo_dtype;
+} isb_gn_bwd_desc;
+int isb_gn_backward(const isb_gn_bwd_desc* d, void* scratch, isb_stream_t stream);
+
+/* ---- attention core (QKVAttentionLegacy, unet.py:337-354) -------------- */
+/* qkv [N,T,3*C] fp32 NHWC-flattened, channel layout per head h:
+ * [h*3*ch, +ch) = q, next ch = k, next ch = v  (legacy interleave, unet.py:346).
+ * out [N,T,C] (out_dtype).  P = softmax_fp32(q k^T / sqrt(ch)) is written to
+ * probs [N,heads,T,T] fp32 and kept for the backward. */
+int isb_attention_forward(const float* qkv, int N, int T, int heads, int ch,
+                          float* probs, void* out, int out_dtype,
+                          isb_stream_t stream);
+/* d_out [N,T,C] fp32 -> d_qkv [N,T,3C] (lo_dtype); tmp [N,heads,T,T] fp32. */
+int isb_attention_backward(const float* qkv, const float* probs,
+                           const float* d_out, int N, int T, int heads, int ch,
+                           float* tmp, void* d_qkv, int lo_dtype,
+                           isb_stream_t stream);
+
+/* ---- timestep embedding path (nn.py:102-120, unet.py:471-475,199-205) --- */
+/* film_all[n, :] = W_all @ silu(W2 @ silu(W1 @ sinus(t[n]) + b1) + b2) + b_all
+ * where W_all/b_all is the row-concatenation of every ResBlock's emb_layers
+ * Linear (rows_all = sum 2*Cout).  All weights fp32 row-major [out,in].
+ * t is a device int64 array of ORIGINAL timesteps (after respace.py:122-126);
+ * freqs [model_ch/2] is the reference's exp(-ln(1e4)*i/half) table (nn.py:113-115)
+ * computed once by the host.  scratch: N * (model_ch + 2*hidden) floats. */
+int isb_time_embed(const int64_t* t, const float* freqs, int N, int model_ch,
+                   int hidden, const float* w1, const float* b1, const float* w2,
+                   const float* b2, const float* w_all, const float* b_all,
+                   int rows_all, float* scratch, float* film_all,
+                   isb_stream_t stream);
+
+/* ---- fused DDPM posterior / guidance update ---------------------------- */
+/* One kernel for gaussian_diffusion.py:265-279,296-317,333-338,208-230,490-506
+ * and drag_utils.py:384-392.  Per-step schedule scalars are read from DEVICE
+ * memory (coef[8], see isb_sched_coef) so that one captured CUDA graph serves
+ * every step index.  model_out is NHWC fp32 with 2*C channels (eps | v).
+ * All image tensors are NCHW fp32 [N,C,H,W] except model_out.
+ *   x_next = mean + nonzero*sqrt(var)*noise + (grad ? var*scale*grad : 0)
+ * Optional outputs (NULL to skip): sample (without guidance), mean, var, x0, eps. */
+enum isb_sched_coef {
+  ISB_SC_SQRT_RECIP_ACP = 0, ISB_SC_SQRT_RECIPM1_ACP = 1,
+  ISB_SC_POST_COEF1 = 2, ISB_SC_POST_COEF2 = 3,
+  ISB_SC_MIN_LOG = 4, ISB_SC_MAX_LOG = 5, ISB_SC_NONZERO = 6, ISB_SC_GUIDE_SCALE = 7
+};
+typedef struct isb_ddpm_desc {
+  const float* x; const float* model_out; int model_out_cstride;
+  const float* noise; const float* grad;
+  const float* coef;  /* device [8] */
+  int N, C, H, W; int clip_denoised;
+  float* x_next; float* sample; float* mean; float* var; float* x0; float* eps;
+} isb_ddpm_desc;
+int isb_ddpm_step(const isb_ddpm_desc* d, isb_stream_t stream);
+
+/* ---- drag guidance: motion supervision + mask regulariser -------------- */
+/* Replaces resize_feat_align + 2x F.grid_sample + masked gathers + the autograd
+ * backward of the loss down to inter_feat (drag_utils.py:141-159,351-383).
+ * feat     : inter_feat of the current step, NHWC fp32 [1,S,S,Cf]
+ * origin   : cached resize_feat_align(inter_feat) of the unedited trajectory,
+ *            plane-major channels-last fp32 [3,S,S,Ca]
+ * chan_map : [3*Ca] int32, feat channel that feeds aligned (plane, a)
+ * inv_map  : [Cf] int32, plane*Ca + a for a feat channel, -1 if resize_feat_align
+ *            drops it (drag_utils.py:146-151)
+ * patch_xy / shift_xy : [3,npts,2] fp32, per-plane 2-D sample points (x->W, y->H)
+ *            in [-1,1]; the (2r+1)^3 lattice of drag_utils.py:316-321 projects to
+ *            (2r+1)^2 distinct points per plane and handle, `weight[npts]` holds
+ *            each point's multiplicity
+ * group_size : points per handle (contiguous), bbox [3,npts/group_size,4] int32 =
+ *            (x0min,x0max,y0min,y0max) over floor() pixel indices of the group's
+ *            shift points (may be conservative)
+ * mask     : [3,S,S] uint8, 1 where the pixel is OUTSIDE the content set
+ *            (drag_utils.py:322-334); mask_count = number of ones
+ * inv_count: 1 / (3*Ca*B*N1)   loss_type 0 = l2, 1 = l1
+ * scratch  : g [3,npts,Ca] f32, pt_info [3,npts,4] f32,
+ *            partial [isb_drag_partial_len()] f64
+ * Writes loss (1 float) and d_feat = dLoss/dfeat NHWC fp32 [1,S,S,Cf] (fully
+ * overwritten, deterministic: gather, no atomics). */
+typedef struct isb_drag_desc {
+  const float* feat; int S; int Cf;
+  const float* origin; int Ca;
+  const int32_t* chan_map; const int32_t* inv_map;
+  const float* patch_xy; const float* shift_xy; const float* weight;
+  int npts; int group_size;
+  const int32_t* bbox;
+  const uint8_t* mask; int mask_count;
+  float inv_count; float cof; int loss_type;
+  float* g; float* pt_info; double* partial; int partial_len;
+  float* loss; float* d_feat;
+} isb_drag_desc;
+size_t isb_drag_partial_len(int S, int Cf, int npts);
+int isb_drag_loss_grad(const isb_drag_desc* d, isb_stream_t stream);
+/* resize_feat_align as a gather: NHWC fp32 [1,S,S,Cf] -> [3,S,S,Ca]. */
+int isb_resize_feat_align(const float* feat, int S, int Cf, const int32_t* chan_map,
+                          float* out, int Ca, isb_stream_t stream);
+
+/* ---- triplane decoder (axisnetworks.py:537-562, visualize.py:79-98) ---- */
+typedef struct isb_triplane_mlp {
+  const float* fourier_B;      /* [32,64] */
+  const float* w1; const float* b1;  /* [128,128],[128] */
+  const float* w2; const float* b2;  /* [128,128],[128] */
+  const float* w3; const float* b3;  /* [1,128],[1] */
+} isb_triplane_mlp;
+/* planes_hwc: [3,R,R,32] fp32 channels-last (isb_nchw_to_nhwc of the reference's
+ * three (1,32,R,R) embeddings).  Dense grid query of lin^3 where lin[res] is the
+ * host's torch.linspace(-1,1,res) table (bit-identical coordinates), index =
+ * x*res^2 + y*res + z (visualize.py:79-86), for x in [x_begin, x_end):
+ * out[(x-x_begin)*res^2 + y*res + z]. */
+int isb_triplane_decode_grid(const float* planes_hwc, int R, const isb_triplane_mlp* w,
+                             const float* lin, int res, int x_begin, int x_end,
+                             float* out, isb_stream_t stream);
+/* Arbitrary points: coords [npts,3] -> out [npts]  (MultiTriplane.forward). */
+int isb_triplane_decode_points(const float* planes_hwc, int R, const isb_triplane_mlp* w,
+                               const float* coords, int64_t npts, float* out,
+                               isb_stream_t stream);
+
+/* ---- introspection ---------------------------------------------------- */
+/* Number of kernels this library has launched in this process (all threads). */
+uint64_t isb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISHAPE_B200_H */

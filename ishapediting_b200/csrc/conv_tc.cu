@@ -1,0 +1,553 @@
+// conv_tc.cu — bf16 implicit-GEMM convolution (3x3 / 1x1 / linear) on the 5th-gen
+// tensor cores: TMA (cp.async.bulk.tensor, 128B swizzle) -> smem ring -> tcgen05.mma
+// with the fp32 accumulator in TMEM -> tcgen05.ld epilogue.
+//
+// GEMM view:  D[M = 128 output pixels, N = block_n output channels] +=
+//             A[M, 64 input channels of one filter tap] * B[N, 64]^T
+// per k-iteration.  The A tile of tap (kh,kw) is the NHWC box
+// {64 ch, tw, th, nb} at (c0, w0+kw-1, h0+kh-1, n0): the TMA zero-fills the halo,
+// so there is no im2col buffer and no materialised padding.  An optional second
+// source (the 1x1 skip convolution of a ResBlock, unet.py:222,256) is appended to
+// the K loop so `skip(x) + h` costs no extra pass.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..5 = epilogue (TMEM lanes 32*(warp%4) ..).  Split-K partials go to a
+// caller workspace and are reduced in fixed order (deterministic).
+#include "common.cuh"
+
+namespace isb {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;
+constexpr int TC_UMMA_K = 16;
+constexpr int TC_A_STAGE = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KiB
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+
+struct TcParams {
+  int tw, th, nb;
+  int tiles_w, tiles_h, tiles_n;
+  int N, H, W;
+  int Cout, block_n;
+  int Cin, chunks0, ntaps, chunks1;
+  int k_iters, splits, stages;
+  int tmem_cols;
+  const float* bias;
+  const float* residual;
+  void* out;
+  int out_dtype;
+  int accumulate;
+  float* partial;  // != nullptr when splits > 1
+};
+
+// ---- PTX wrappers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a pipeline bug must trap (CUDA error to the caller), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0 && global_timer_ns() - t0 > 2000000000ull) __trap();
+  }
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(m), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);  // [0,14)  start address >> 4
+  d |= static_cast<uint64_t>(1) << 16;                   // [16,30) LBO (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;           // [32,46) SBO = 1024 B
+  d |= static_cast<uint64_t>(1) << 46;                   // [46,48) descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                   // [61,64) SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- the kernel -------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
+               const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
+  const uint32_t stage_bytes = TC_A_STAGE + static_cast<uint32_t>(p.block_n) * 128u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // output tile of this CTA
+  int mt = blockIdx.x;
+  const int tile_w = mt % p.tiles_w;
+  mt /= p.tiles_w;
+  const int tile_h = mt % p.tiles_h;
+  const int tile_n = mt / p.tiles_h;
+  const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.nb;
+  const int cout0 = blockIdx.y * p.block_n;
+  const int split = blockIdx.z;
+  const int k_begin = static_cast<int>(static_cast<long long>(p.k_iters) * split / p.splits);
+  const int k_end = static_cast<int>(static_cast<long long>(p.k_iters) * (split + 1) / p.splits);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapA2);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_slot)),
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const int seg0_iters = p.ntaps * p.chunks0;
+      for (int it = k_begin; it < k_end; ++it) {
+        const int i = it - k_begin;
+        const int s = i % p.stages;
+        const uint32_t ph = static_cast<uint32_t>(i / p.stages) & 1u;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_expect_tx(fb, stage_bytes);
+        const uint32_t a_dst = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
+        const uint32_t b_dst = a_dst + TC_A_STAGE;
+        if (it < seg0_iters) {
+          const int tap = it / p.chunks0;
+          const int chunk = it - tap * p.chunks0;
+          int dh = 0, dw = 0;
+          if (p.ntaps == 9) {
+            dh = tap / 3 - 1;
+            dw = tap % 3 - 1;
+          }
+          tma_load_4d(a_dst, &mapA, fb, chunk * TC_BLOCK_K, w0 + dw, h0 + dh, n0);
+          tma_load_2d(b_dst, &mapB, fb, tap * p.Cin + chunk * TC_BLOCK_K, cout0);
+        } else {
+          const int chunk = it - seg0_iters;
+          tma_load_4d(a_dst, &mapA2, fb, chunk * TC_BLOCK_K, w0, h0, n0);
+          tma_load_2d(b_dst, &mapB, fb, p.ntaps * p.Cin + chunk * TC_BLOCK_K, cout0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, K-major both, N=block_n, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                             (static_cast<uint32_t>(p.block_n >> 3) << 17) |
+                             (static_cast<uint32_t>(TC_BLOCK_M >> 4) << 24);
+      for (int it = k_begin; it < k_end; ++it) {
+        const int i = it - k_begin;
+        const int s = i % p.stages;
+        const uint32_t ph = static_cast<uint32_t>(i / p.stages) & 1u;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t a_addr = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
+        const uint64_t adesc = make_desc_sw128(a_addr);
+        const uint64_t bdesc = make_desc_sw128(a_addr + TC_A_STAGE);
+#pragma unroll
+        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+          // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
+          umma_bf16(tmem_base, adesc + static_cast<uint64_t>(k * 2),
+                    bdesc + static_cast<uint64_t>(k * 2), idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));  // frees the smem slot when these MMAs retire
+      }
+      umma_commit(smem_u32(&tmem_full_bar));   // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps 2..5 =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int per_img = p.tw * p.th;
+    const int pn = r / per_img;
+    const int rem = r - pn * per_img;
+    const int ph_ = rem / p.tw;
+    const int pw_ = rem - ph_ * p.tw;
+    const int n = n0 + pn;
+    const bool valid = n < p.N;
+    const size_t m = (static_cast<size_t>(n) * p.H + (h0 + ph_)) * p.W + (w0 + pw_);
+    const size_t m_total = static_cast<size_t>(p.N) * p.H * p.W;
+
+    mbar_wait(smem_u32(&tmem_full_bar), 0);
+    tc_fence_after();
+    const int nchunks = p.block_n / 32;
+    for (int c = 0; c < nchunks; ++c) {
+      const int col0 = cout0 + c * 32;
+      if (col0 >= p.Cout) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
+      tmem_ld_wait();
+      if (!valid) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.partial != nullptr) {
+        float4* dst = reinterpret_cast<float4*>(p.partial + (static_cast<size_t>(split) * m_total + m) * p.Cout + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        continue;
+      }
+      const size_t off = m * p.Cout + col0;
+      if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+        }
+      }
+      if (p.residual != nullptr) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.residual + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(r4 + j);
+          f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+        }
+      }
+      if (p.out_dtype == ISB_BF16) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+          u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+          u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+          u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+          dst[j] = u;
+        }
+      } else {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+        if (p.accumulate) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 o = dst[j];
+            f[4 * j] += o.x; f[4 * j + 1] += o.y; f[4 * j + 2] += o.z; f[4 * j + 3] += o.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
+                 : "memory");
+  }
+}
+
+// out = (acc ? out : 0) + bias + residual + sum_s partial[s]   (fixed order: deterministic)
+__global__ void __launch_bounds__(256)
+splitk_finalize_kernel(const float* __restrict__ partial, int splits, size_t m_total, int Cout,
+                       const float* __restrict__ bias, const float* __restrict__ residual, void* out,
+                       int out_dtype, int accumulate) {
+  const size_t total8 = m_total * Cout / 8;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total8) return;
+  const size_t e = idx * 8;
+  const int col = static_cast<int>(e % Cout);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const size_t plane = m_total * Cout;
+  for (int s = 0; s < splits; ++s) {
+    float v[8];
+    load8(partial + s * plane + e, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+  if (bias) {
+    float v[8];
+    load8(bias + col, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+  if (residual) {
+    float v[8];
+    load8(residual + e, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+  if (accumulate && out_dtype == ISB_F32) {
+    const float4* o = reinterpret_cast<const float4*>(reinterpret_cast<float*>(out) + e);
+    const float4 a = o[0], b = o[1];
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+  store8(out, e, out_dtype, acc);
+}
+
+// ---- host side --------------------------------------------------------------
+struct TcPlan {
+  TcParams p;
+  int smem_bytes;
+  size_t ws_bytes;
+  dim3 grid;
+};
+
+static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
+  ISB_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "conv_tc: ksize %d unsupported", d->ksize);
+  ISB_CHECK_ARG(d->Cin > 0 && d->Cin % 64 == 0, "conv_tc: Cin=%d must be a multiple of 64", d->Cin);
+  ISB_CHECK_ARG(d->a2 == nullptr || (d->Cin2 > 0 && d->Cin2 % 64 == 0),
+                "conv_tc: Cin2=%d must be a multiple of 64", d->Cin2);
+  ISB_CHECK_ARG(d->Cout > 0 && d->Cout % 32 == 0, "conv_tc: Cout=%d must be a multiple of 32", d->Cout);
+  ISB_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0, "conv_tc: bad N/H/W");
+  TcParams& p = plan->p;
+  p.N = d->N; p.H = d->H; p.W = d->W;
+  // spatial tile of 128 output pixels
+  if (d->W >= 128) {
+    ISB_CHECK_ARG(d->W % 128 == 0, "conv_tc: W=%d must be a power of two <= 128 or a multiple of 128", d->W);
+    p.tw = 128;
+  } else {
+    ISB_CHECK_ARG((d->W & (d->W - 1)) == 0 && d->W >= 8, "conv_tc: W=%d must be a power of two >= 8", d->W);
+    p.tw = d->W;
+  }
+  p.th = 128 / p.tw;
+  if (p.th > d->H) {
+    ISB_CHECK_ARG((d->H & (d->H - 1)) == 0, "conv_tc: H=%d must be a power of two when H*W < 128", d->H);
+    p.th = d->H;
+  }
+  ISB_CHECK_ARG(d->H % p.th == 0, "conv_tc: H=%d not divisible by tile height %d", d->H, p.th);
+  p.nb = 128 / (p.tw * p.th);
+  p.tiles_w = d->W / p.tw;
+  p.tiles_h = d->H / p.th;
+  p.tiles_n = cdiv(d->N, p.nb);
+  p.Cout = d->Cout;
+  p.Cin = d->Cin;
+  p.chunks0 = d->Cin / 64;
+  p.ntaps = d->ksize * d->ksize;
+  p.chunks1 = d->a2 ? d->Cin2 / 64 : 0;
+  p.k_iters = p.ntaps * p.chunks0 + p.chunks1;
+  const int mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  // N tile
+  int bn = d->block_n;
+  if (bn == 0) {
+    if (d->Cout < 128) bn = d->Cout;                                  // 32,64,96
+    else if (d->Cout % 128 != 0 && d->Cout <= 256) bn = d->Cout;      // e.g. 192: one exact tile
+    else bn = 128;
+    if (d->Cout % 256 == 0 && static_cast<long long>(mtiles) * (d->Cout / 128) >= 4LL * num_sms()) bn = 256;
+  }
+  ISB_CHECK_ARG(bn >= 32 && bn <= 256 && bn % 32 == 0, "conv_tc: block_n=%d must be a multiple of 32 in [32,256]", bn);
+  p.block_n = bn;
+  p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
+  const int ntiles = cdiv(d->Cout, bn);
+  const int tiles = mtiles * ntiles;
+  int splits = d->split_k;
+  if (splits == 0) {
+    splits = 1;
+    if (tiles < (num_sms() * 3) / 4) {
+      splits = cdiv(num_sms(), tiles);
+      if (splits > p.k_iters / 2) splits = p.k_iters / 2;
+      if (splits > 32) splits = 32;
+      if (splits < 1) splits = 1;
+    }
+  }
+  ISB_CHECK_ARG(splits >= 1 && splits <= p.k_iters, "conv_tc: split_k=%d out of range (k_iters=%d)", splits, p.k_iters);
+  p.splits = splits;
+  const int stage_bytes = TC_A_STAGE + bn * 128;
+  int stages = d->stages;
+  if (stages == 0) stages = bn <= 128 ? 3 : 4;
+  const int max_stages = (TC_SMEM_LIMIT - 1024) / stage_bytes;
+  if (stages > max_stages) stages = max_stages;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  ISB_CHECK_ARG(stages >= 2, "conv_tc: not enough shared memory for 2 stages");
+  p.stages = stages;
+  plan->smem_bytes = stages * stage_bytes + 1024;
+  plan->ws_bytes = splits > 1 ? static_cast<size_t>(splits) * d->N * d->H * d->W * d->Cout * sizeof(float) : 0;
+  plan->grid = dim3(mtiles, ntiles, splits);
+  p.bias = d->bias;
+  p.residual = d->residual;
+  p.out = d->out;
+  p.out_dtype = d->out_dtype;
+  p.accumulate = d->accumulate;
+  p.partial = nullptr;
+  return ISB_OK;
+}
+
+static int encode_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int tw, int th,
+                          int nb) {
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_tensormap_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim,
+                                      gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%d, box 64x%dx%dx%d) failed: %d", N, H, W, C, tw, th,
+              nb, (int)r);
+    return ISB_ERR_CUDA;
+  }
+  return ISB_OK;
+}
+
+static int encode_weight_map(CUtensorMap* m, const void* ptr, int Cout, int Ktot, int bn) {
+  cuuint64_t gdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+  cuuint64_t gstr[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_tensormap_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim,
+                                      gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weight %dx%d, box 64x%d) failed: %d", Cout, Ktot, bn, (int)r);
+    return ISB_ERR_CUDA;
+  }
+  return ISB_OK;
+}
+
+int conv_tc_init() {
+  ISB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+  return ISB_OK;
+}
+
+size_t conv_tc_workspace(const isb_conv_desc* d) {
+  TcPlan plan;
+  if (plan_tc(d, &plan) != ISB_OK) return 0;
+  return plan.ws_bytes;
+}
+
+int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  TcPlan plan;
+  int rc = plan_tc(d, &plan);
+  if (rc) return rc;
+  ISB_CHECK_ARG(d->out_dtype == ISB_F32 || d->out_dtype == ISB_BF16, "conv_tc: bad out dtype");
+  ISB_CHECK_ARG(!(d->accumulate && d->out_dtype != ISB_F32), "conv_tc: accumulate needs fp32 out");
+  ISB_CHECK_ARG((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+                "conv_tc: pointers must be 16-byte aligned");
+  TcParams& p = plan.p;
+  if (p.splits > 1) {
+    if (ws == nullptr || ws_bytes < plan.ws_bytes) {
+      set_error("conv_tc: workspace %zu bytes < required %zu", ws_bytes, plan.ws_bytes);
+      return ISB_ERR_WORKSPACE;
+    }
+    p.partial = static_cast<float*>(ws);
+  }
+  CUtensorMap mapA, mapA2, mapB;
+  rc = encode_act_map(&mapA, d->a, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.nb);
+  if (rc) return rc;
+  if (d->a2) {
+    rc = encode_act_map(&mapA2, d->a2, d->N, d->H, d->W, d->Cin2, p.tw, p.th, p.nb);
+    if (rc) return rc;
+  } else {
+    mapA2 = mapA;
+  }
+  const int Ktot = p.ntaps * d->Cin + (d->a2 ? d->Cin2 : 0);
+  rc = encode_weight_map(&mapB, d->w, d->Cout, Ktot, p.block_n);
+  if (rc) return rc;
+  conv_tc_kernel<<<plan.grid, TC_THREADS, plan.smem_bytes, stream>>>(mapA, mapA2, mapB, p);
+  ISB_LAUNCH_CHECK();
+  if (p.splits > 1) {
+    const size_t m_total = static_cast<size_t>(d->N) * d->H * d->W;
+    const size_t total8 = m_total * d->Cout / 8;
+    splitk_finalize_kernel<<<cdiv(total8, 256), 256, 0, stream>>>(p.partial, p.splits, m_total, d->Cout, d->bias,
+                                                                  d->residual, d->out, d->out_dtype,
+                                                                  d->accumulate);
+    ISB_LAUNCH_CHECK();
+  }
+  return ISB_OK;
+}
+
+}  // namespace isb

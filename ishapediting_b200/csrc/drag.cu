@@ -1,0 +1,230 @@
+// drag.cu — drag guidance: motion-supervision loss + mask regulariser and their analytic
+// gradient w.r.t. the intermediate UNet feature (drag_utils.py:141-159, 351-383).
+//
+// The reference materialises resize_feat_align (permute/interpolate/cat), two
+// (3,170,B,15625) grid_sample outputs and lets autograd scatter-add the gradient back.  Here:
+//   * resize_feat_align is an index map (chan_map / inv_map) applied on the fly;
+//   * the (2r+1)^3 patch lattice projects onto (2r+1)^2 distinct 2-D points per plane and
+//     handle, each with multiplicity (2r+1): the host passes the distinct points + weights;
+//   * kernel 1 samples origin@patch and edit@shift bilinearly (align_corners=True, zeros
+//     padding) and stores the per-point loss derivative g;
+//   * kernel 2 is a GATHER over feature pixels (no atomics -> bit-reproducible): each pixel
+//     walks the points of the handles whose bounding box covers it, adds the mask-regulariser
+//     term and writes dLoss/dfeat straight into the NHWC feature gradient;
+//   * kernel 3 folds the loss partials in fixed order.
+#include "common.cuh"
+
+namespace isb {
+
+struct DragArgs {
+  const float* feat; int S; int Cf;
+  const float* origin; int Ca;
+  const int32_t* chan_map; const int32_t* inv_map;
+  const float* patch_xy; const float* shift_xy; const float* weight;
+  int npts; int group_size; int ngroups;
+  const int32_t* bbox;
+  const uint8_t* mask; int mask_count;
+  float inv_count; float cof; int loss_type;
+  float* g; float* pt_info; double* partial; int n_gather_blocks;
+  float* loss; float* d_feat;
+};
+
+struct Bilin {
+  int x0, y0;
+  float fx, fy;
+};
+// torch grid_sampler_compute_source_index, align_corners=True
+__device__ __forceinline__ Bilin bilin_setup(float gx, float gy, int S) {
+  const float ix = ((gx + 1.0f) / 2.0f) * static_cast<float>(S - 1);
+  const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(S - 1);
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  Bilin b;
+  b.x0 = static_cast<int>(fx0);
+  b.y0 = static_cast<int>(fy0);
+  b.fx = ix - fx0;
+  b.fy = iy - fy0;
+  return b;
+}
+
+// grid (npts, 3); block loops over the Ca aligned channels
+__global__ void __launch_bounds__(192)
+drag_sample_kernel(const DragArgs a) {
+  const int j = blockIdx.x, pl = blockIdx.y;
+  const int S = a.S;
+  const size_t pj = static_cast<size_t>(pl) * a.npts + j;
+  const Bilin bp = bilin_setup(a.patch_xy[pj * 2], a.patch_xy[pj * 2 + 1], S);
+  const Bilin bs = bilin_setup(a.shift_xy[pj * 2], a.shift_xy[pj * 2 + 1], S);
+  const float wt = a.weight[j];
+  if (threadIdx.x == 0) {
+    float4 info = make_float4(static_cast<float>(bs.x0), static_cast<float>(bs.y0), bs.fx, bs.fy);
+    reinterpret_cast<float4*>(a.pt_info)[pj] = info;
+  }
+  float lsum = 0.f;
+  for (int ch = threadIdx.x; ch < a.Ca; ch += blockDim.x) {
+    float pv = 0.f, sv = 0.f;
+    const int src_c = a.chan_map[pl * a.Ca + ch];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        {
+          const int x = bp.x0 + dx, y = bp.y0 + dy;
+          if (x >= 0 && x < S && y >= 0 && y < S) {
+            const float w = (dx ? bp.fx : 1.0f - bp.fx) * (dy ? bp.fy : 1.0f - bp.fy);
+            pv = fmaf(w, __ldg(a.origin + ((static_cast<size_t>(pl) * S + y) * S + x) * a.Ca + ch), pv);
+          }
+        }
+        {
+          const int x = bs.x0 + dx, y = bs.y0 + dy;
+          if (x >= 0 && x < S && y >= 0 && y < S) {
+            const float w = (dx ? bs.fx : 1.0f - bs.fx) * (dy ? bs.fy : 1.0f - bs.fy);
+            sv = fmaf(w, __ldg(a.feat + (static_cast<size_t>(y) * S + x) * a.Cf + src_c), sv);
+          }
+        }
+      }
+    const float diff = sv - pv;
+    float gv;
+    if (a.loss_type == 0) { gv = 2.0f * diff; lsum = fmaf(diff, diff, lsum); }
+    else { gv = static_cast<float>((diff > 0.f) - (diff < 0.f)); lsum += fabsf(diff); }
+    a.g[pj * a.Ca + ch] = wt * gv;
+  }
+  __shared__ float red[6];
+  lsum = warp_sum(lsum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+    a.partial[pj] = s * wt;
+  }
+}
+
+// one thread per (pixel, feature channel)
+__global__ void __launch_bounds__(256)
+drag_gather_kernel(const DragArgs a) {
+  const int S = a.S;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(S) * S * a.Cf;
+  float msq = 0.f;
+  if (idx < total) {
+    const int c = static_cast<int>(idx % a.Cf);
+    const int pix = static_cast<int>(idx / a.Cf);
+    const int x = pix % S, y = pix / S;
+    const int m = a.inv_map[c];
+    float d = 0.f;
+    if (m >= 0) {
+      const int pl = m / a.Ca, ch = m - pl * a.Ca;
+      float acc = 0.f;
+      for (int grp = 0; grp < a.ngroups; ++grp) {
+        const int4 bb = __ldg(reinterpret_cast<const int4*>(a.bbox) + pl * a.ngroups + grp);
+        if (x < bb.x || x > bb.y + 1 || y < bb.z || y > bb.w + 1) continue;
+        const int jbeg = grp * a.group_size;
+        for (int jj = 0; jj < a.group_size; ++jj) {
+          const size_t pj = static_cast<size_t>(pl) * a.npts + jbeg + jj;
+          const float4 info = reinterpret_cast<const float4*>(a.pt_info)[pj];
+          const int x0 = static_cast<int>(info.x), y0 = static_cast<int>(info.y);
+          const int ddx = x - x0, ddy = y - y0;
+          if (ddx < 0 || ddx > 1 || ddy < 0 || ddy > 1) continue;
+          const float w = (ddx ? info.z : 1.0f - info.z) * (ddy ? info.w : 1.0f - info.w);
+          acc = fmaf(w, a.g[pj * a.Ca + ch], acc);
+        }
+      }
+      d = -a.inv_count * acc;
+      if (a.cof > 0.f && a.mask[(static_cast<size_t>(pl) * S + y) * S + x]) {
+        const float e = a.feat[idx];
+        const float o = __ldg(a.origin + ((static_cast<size_t>(pl) * S + y) * S + x) * a.Ca + ch);
+        const float df = e - o;
+        const float norm = 1.0f / (static_cast<float>(a.Ca) * static_cast<float>(a.mask_count));
+        if (a.loss_type == 0) { d -= a.cof * 2.0f * df * norm; msq = df * df; }
+        else { d -= a.cof * static_cast<float>((df > 0.f) - (df < 0.f)) * norm; msq = fabsf(df); }
+      }
+    }
+    a.d_feat[idx] = d;
+  }
+  __shared__ float red[8];
+  msq = warp_sum(msq);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = msq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    a.partial[static_cast<size_t>(3) * a.npts + blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+drag_loss_kernel(const DragArgs a) {
+  __shared__ double red[2][8];
+  double motion = 0, mask = 0;
+  const int n_motion = 3 * a.npts;
+  for (int i = threadIdx.x; i < n_motion; i += blockDim.x) motion += a.partial[i];
+  for (int i = threadIdx.x; i < a.n_gather_blocks; i += blockDim.x) mask += a.partial[n_motion + i];
+  motion = warp_sum_d(motion);
+  mask = warp_sum_d(mask);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = motion; red[1][threadIdx.x >> 5] = mask; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mo = 0, ma = 0;
+    for (int w = 0; w < 8; ++w) { mo += red[0][w]; ma += red[1][w]; }
+    double loss = -mo * static_cast<double>(a.inv_count);
+    if (a.cof > 0.f && a.mask_count > 0) loss -= static_cast<double>(a.cof) * ma / (static_cast<double>(a.Ca) * a.mask_count);
+    *a.loss = static_cast<float>(loss);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+resize_feat_align_kernel(const float* __restrict__ feat, int S, int Cf, const int32_t* __restrict__ chan_map,
+                         float* __restrict__ out, int Ca) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = 3LL * S * S * Ca;
+  if (idx >= total) return;
+  const int ch = static_cast<int>(idx % Ca);
+  const long long t = idx / Ca;
+  const int pix = static_cast<int>(t % (S * S));
+  const int pl = static_cast<int>(t / (S * S));
+  out[idx] = __ldg(feat + static_cast<size_t>(pix) * Cf + chan_map[pl * Ca + ch]);
+}
+
+}  // namespace isb
+
+extern "C" {
+
+size_t isb_drag_partial_len(int S, int Cf, int npts) {
+  const long long total = static_cast<long long>(S) * S * Cf;
+  return static_cast<size_t>(3) * npts + static_cast<size_t>((total + 255) / 256);
+}
+
+int isb_drag_loss_grad(const isb_drag_desc* d, isb_stream_t stream) {
+  ISB_CHECK_ARG(d && d->feat && d->origin && d->chan_map && d->inv_map && d->patch_xy && d->shift_xy && d->weight &&
+                    d->bbox && d->g && d->pt_info && d->partial && d->loss && d->d_feat,
+                "isb_drag_loss_grad: null pointer");
+  ISB_CHECK_ARG(d->S > 1 && d->Cf > 0 && d->Ca > 0 && d->npts > 0, "isb_drag_loss_grad: bad shape");
+  ISB_CHECK_ARG(d->group_size > 0 && d->npts % d->group_size == 0, "isb_drag_loss_grad: npts must be a multiple of group_size");
+  ISB_CHECK_ARG(d->cof <= 0.f || (d->mask != nullptr && d->mask_count > 0), "isb_drag_loss_grad: mask required when cof > 0");
+  const long long total = static_cast<long long>(d->S) * d->S * d->Cf;
+  const int gblocks = isb::cdiv(total, 256);
+  ISB_CHECK_ARG(static_cast<size_t>(d->partial_len) >= isb_drag_partial_len(d->S, d->Cf, d->npts), "isb_drag_loss_grad: partial buffer too small");
+  isb::DragArgs a{d->feat, d->S, d->Cf, d->origin, d->Ca, d->chan_map, d->inv_map,
+                  d->patch_xy, d->shift_xy, d->weight, d->npts, d->group_size, d->npts / d->group_size,
+                  d->bbox, d->mask, d->mask_count, d->inv_count, d->cof, d->loss_type,
+                  d->g, d->pt_info, d->partial, gblocks, d->loss, d->d_feat};
+  cudaStream_t st = isb::as_stream(stream);
+  isb::drag_sample_kernel<<<dim3(d->npts, 3), 192, 0, st>>>(a);
+  ISB_LAUNCH_CHECK();
+  isb::drag_gather_kernel<<<gblocks, 256, 0, st>>>(a);
+  ISB_LAUNCH_CHECK();
+  isb::drag_loss_kernel<<<1, 256, 0, st>>>(a);
+  ISB_LAUNCH_CHECK();
+  return ISB_OK;
+}
+
+int isb_resize_feat_align(const float* feat, int S, int Cf, const int32_t* chan_map, float* out, int Ca,
+                          isb_stream_t stream) {
+  ISB_CHECK_ARG(feat && chan_map && out && S > 0 && Cf > 0 && Ca > 0, "isb_resize_feat_align: bad args");
+  const long long total = 3LL * S * S * Ca;
+  isb::resize_feat_align_kernel<<<isb::cdiv(total, 256), 256, 0, isb::as_stream(stream)>>>(feat, S, Cf, chan_map, out, Ca);
+  ISB_LAUNCH_CHECK();
+  return ISB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,389 @@
+// groupnorm.cu — GroupNorm32 (+FiLM scale/shift) (+SiLU) (+2x avg-pool / nearest-up) over a
+// (possibly two-source, i.e. channel-concatenated) fp32 NHWC tensor, forward and input-gradient
+// backward.  HBM-bound: every thread owns 8 consecutive channels of one pixel (32 B fp32 loads,
+// 16 B bf16 stores); statistics are reduced in two deterministic stages (per-block partials in
+// double, the last-arriving block of a group folds them in fixed order).
+//
+// Reference: nn.py:16-18 (GroupNorm32, fp32 math), unet.py:183-184,207-208,245-253 (ResBlock
+// in/out layers with FiLM), unet.py:285 (attention norm), unet.py:613-614 (out), and
+// unet.py:107,136 (nearest 2x / avg-pool inside up/down ResBlocks).
+#include "common.cuh"
+
+namespace isb {
+
+constexpr int GN_MAX_SPLITS = 64;
+
+struct GnArgs {
+  const float* x1; const float* x2;
+  int C1, C2, C, Cg, groups;
+  int N, H, W, HW;
+  float eps;
+  const float* gamma; const float* beta;
+  const float* film; int film_stride;
+  int silu, resample;
+  float* stats;       // [N,G,2] mean,rstd
+  // scratch
+  int* counters;      // [N*G]
+  double2* partials;  // [N*G*GN_MAX_SPLITS]
+  float* bstats;      // [N,G,2]  (backward: s1, s2)
+  int splits;
+};
+
+__device__ __forceinline__ void gn_load_x8(const GnArgs& a, int n, int pix, int c0, float* v) {
+  if (c0 < a.C1) load8(a.x1 + (static_cast<size_t>(n) * a.HW + pix) * a.C1 + c0, v);
+  else load8(a.x2 + (static_cast<size_t>(n) * a.HW + pix) * a.C2 + (c0 - a.C1), v);
+}
+// effective per-(n,c) affine: z = xhat * ga + be
+__device__ __forceinline__ void gn_affine8(const GnArgs& a, int n, int c0, float* ga, float* be) {
+  load8(a.gamma + c0, ga);
+  load8(a.beta + c0, be);
+  if (a.film != nullptr) {
+    float sc[8], sh[8];
+    load8(a.film + static_cast<size_t>(n) * a.film_stride + c0, sc);
+    load8(a.film + static_cast<size_t>(n) * a.film_stride + a.C + c0, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ga[j] = ga[j] * (1.0f + sc[j]);
+      be[j] = be[j] * (1.0f + sc[j]) + sh[j];
+    }
+  }
+}
+
+// Fold per-block partials: the last block to arrive for group (n,g) sums them in index order.
+// Returns true in thread 0 of that last block with the totals in (t0,t1).
+__device__ __forceinline__ bool gn_block_reduce_and_fold(const GnArgs& a, int ng, int split, double v0, double v1,
+                                                         double& t0, double& t1) {
+  __shared__ double sh0[8], sh1[8];
+  __shared__ int is_last;
+  v0 = warp_sum_d(v0);
+  v1 = warp_sum_d(v1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh0[warp] = v0; sh1[warp] = v1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0, s1 = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { s0 += sh0[w]; s1 += sh1[w]; }
+    a.partials[static_cast<size_t>(ng) * GN_MAX_SPLITS + split] = make_double2(s0, s1);
+    __threadfence();
+    const int prev = atomicAdd(a.counters + ng, 1);
+    is_last = (prev == a.splits - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return false;
+  __threadfence();
+  double s0 = 0, s1 = 0;
+  const volatile double2* pp = a.partials + static_cast<size_t>(ng) * GN_MAX_SPLITS;
+  for (int s = 0; s < a.splits; ++s) { s0 += pp[s].x; s1 += pp[s].y; }
+  a.counters[ng] = 0;  // leave the scratch zeroed for the next call
+  t0 = s0; t1 = s1;
+  return true;
+}
+
+// grid (splits, G, N)
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const GnArgs a) {
+  const int split = blockIdx.x, g = blockIdx.y, n = blockIdx.z;
+  const int V = a.Cg / 8;
+  const long long total = static_cast<long long>(a.HW) * V;
+  const long long beg = total * split / a.splits, end = total * (split + 1) / a.splits;
+  float s = 0.f, ss = 0.f;
+  for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const int pix = static_cast<int>(i / V);
+    const int c0 = g * a.Cg + static_cast<int>(i % V) * 8;
+    float v[8];
+    gn_load_x8(a, n, pix, c0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += v[j]; ss = fmaf(v[j], v[j], ss); }
+  }
+  double t0, t1;
+  if (gn_block_reduce_and_fold(a, n * a.groups + g, split, static_cast<double>(s), static_cast<double>(ss), t0, t1)) {
+    const double m = static_cast<double>(a.HW) * a.Cg;
+    const double mean = t0 / m;
+    double var = t1 / m - mean * mean;
+    if (var < 0) var = 0;
+    a.stats[(n * a.groups + g) * 2 + 0] = static_cast<float>(mean);
+    a.stats[(n * a.groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  }
+}
+
+struct GnFwdOut {
+  void* y; int y_dtype;
+  void* raw; int raw_dtype;
+  float* xres;
+};
+
+// z/act for 8 channels of one input pixel
+__device__ __forceinline__ void gn_act8(const GnArgs& a, const float* x, float mean, float rstd, const float* ga,
+                                        const float* be, float* out) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float z = (x[j] - mean) * rstd * ga[j] + be[j];
+    out[j] = a.silu ? silu_f(z) : z;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const GnArgs a, const GnFwdOut o) {
+  const int CV = a.C / 8;
+  const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;  // thread grid
+  const long long total = static_cast<long long>(a.N) * Ho * Wo * CV;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = static_cast<int>(idx % CV);
+  long long t = idx / CV;
+  const int w = static_cast<int>(t % Wo); t /= Wo;
+  const int h = static_cast<int>(t % Ho);
+  const int n = static_cast<int>(t / Ho);
+  const int c0 = cv * 8;
+  const int g = c0 / a.Cg;
+  const float mean = a.stats[(n * a.groups + g) * 2], rstd = a.stats[(n * a.groups + g) * 2 + 1];
+  float ga[8], be[8];
+  gn_affine8(a, n, c0, ga, be);
+  if (a.resample == 0) {
+    const int pix = h * a.W + w;
+    float x[8], y[8];
+    gn_load_x8(a, n, pix, c0, x);
+    gn_act8(a, x, mean, rstd, ga, be, y);
+    const size_t off = (static_cast<size_t>(n) * a.HW + pix) * a.C + c0;
+    store8(o.y, off, o.y_dtype, y);
+    if (o.raw) store8(o.raw, off, o.raw_dtype, x);
+  } else if (a.resample == 1) {  // 2x2 average pool of the activation (and of x for the skip)
+    float ysum[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int pix = (2 * h + dy) * a.W + (2 * w + dx);
+        float x[8], y[8];
+        gn_load_x8(a, n, pix, c0, x);
+        gn_act8(a, x, mean, rstd, ga, be, y);
+        if (o.raw) store8(o.raw, (static_cast<size_t>(n) * a.HW + pix) * a.C + c0, o.raw_dtype, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ysum[j] += y[j]; xsum[j] += x[j]; }
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ysum[j] *= 0.25f; xsum[j] *= 0.25f; }
+    const size_t off = ((static_cast<size_t>(n) * Ho + h) * Wo + w) * a.C + c0;
+    store8(o.y, off, o.y_dtype, ysum);
+    if (o.xres) store8(o.xres, off, ISB_F32, xsum);
+  } else {  // nearest 2x upsample
+    const int pix = h * a.W + w;
+    float x[8], y[8];
+    gn_load_x8(a, n, pix, c0, x);
+    gn_act8(a, x, mean, rstd, ga, be, y);
+    if (o.raw) store8(o.raw, (static_cast<size_t>(n) * a.HW + pix) * a.C + c0, o.raw_dtype, x);
+    const int H2 = a.H * 2, W2 = a.W * 2;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const size_t off = ((static_cast<size_t>(n) * H2 + (2 * h + dy)) * W2 + (2 * w + dx)) * a.C + c0;
+        store8(o.y, off, o.y_dtype, y);
+        if (o.xres) store8(o.xres, off, ISB_F32, x);
+      }
+  }
+}
+
+// ---- backward ---------------------------------------------------------------
+struct GnBwdArgs {
+  const float* dy;
+  const float* gres; int gres_at_input;
+  float* gx1; int acc1; void* gx1_lo;
+  float* gx2; int acc2; void* gx2_lo;
+  int lo_dtype;
+};
+
+// gradient arriving at input pixel (h,w) from a tensor living at OUTPUT resolution, pulled back
+// through the resample (transpose of avg-pool / nearest-up).
+__device__ __forceinline__ void gn_pull8(const GnArgs& a, const float* src, int n, int h, int w, int c0, float* v) {
+  if (a.resample == 0) {
+    load8(src + ((static_cast<size_t>(n) * a.H + h) * a.W + w) * a.C + c0, v);
+  } else if (a.resample == 1) {
+    const int Ho = a.H / 2, Wo = a.W / 2;
+    load8(src + ((static_cast<size_t>(n) * Ho + (h >> 1)) * Wo + (w >> 1)) * a.C + c0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= 0.25f;
+  } else {
+    const int H2 = a.H * 2, W2 = a.W * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float t[8];
+        load8(src + ((static_cast<size_t>(n) * H2 + (2 * h + dy)) * W2 + (2 * w + dx)) * a.C + c0, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += t[j];
+      }
+  }
+}
+
+// dz * gamma'' and xhat for 8 channels
+__device__ __forceinline__ void gn_bwd_terms8(const GnArgs& a, const GnBwdArgs& b, int n, int h, int w, int c0,
+                                              float mean, float rstd, float* dzg, float* xhat) {
+  float x[8], ga[8], be[8], dy[8];
+  gn_load_x8(a, n, h * a.W + w, c0, x);
+  gn_affine8(a, n, c0, ga, be);
+  gn_pull8(a, b.dy, n, h, w, c0, dy);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    xhat[j] = (x[j] - mean) * rstd;
+    float d = dy[j];
+    if (a.silu) d *= silu_grad_f(xhat[j] * ga[j] + be[j]);
+    dzg[j] = d * ga[j];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_bwd_reduce_kernel(const GnArgs a, const GnBwdArgs b) {
+  const int split = blockIdx.x, g = blockIdx.y, n = blockIdx.z;
+  const int V = a.Cg / 8;
+  const long long total = static_cast<long long>(a.HW) * V;
+  const long long beg = total * split / a.splits, end = total * (split + 1) / a.splits;
+  const float mean = a.stats[(n * a.groups + g) * 2], rstd = a.stats[(n * a.groups + g) * 2 + 1];
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const int pix = static_cast<int>(i / V);
+    const int c0 = g * a.Cg + static_cast<int>(i % V) * 8;
+    float dzg[8], xhat[8];
+    gn_bwd_terms8(a, b, n, pix / a.W, pix % a.W, c0, mean, rstd, dzg, xhat);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 += dzg[j]; s2 = fmaf(dzg[j], xhat[j], s2); }
+  }
+  double t0, t1;
+  if (gn_block_reduce_and_fold(a, n * a.groups + g, split, static_cast<double>(s1), static_cast<double>(s2), t0, t1)) {
+    const double m = static_cast<double>(a.HW) * a.Cg;
+    a.bstats[(n * a.groups + g) * 2 + 0] = static_cast<float>(t0 / m);
+    a.bstats[(n * a.groups + g) * 2 + 1] = static_cast<float>(t1 / m);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const GnArgs a, const GnBwdArgs b) {
+  const int CV = a.C / 8;
+  const long long total = static_cast<long long>(a.N) * a.HW * CV;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = static_cast<int>(idx % CV);
+  long long t = idx / CV;
+  const int w = static_cast<int>(t % a.W); t /= a.W;
+  const int h = static_cast<int>(t % a.H);
+  const int n = static_cast<int>(t / a.H);
+  const int c0 = cv * 8;
+  const int g = c0 / a.Cg;
+  const int sg = n * a.groups + g;
+  const float mean = a.stats[sg * 2], rstd = a.stats[sg * 2 + 1];
+  const float m1 = a.bstats[sg * 2], m2 = a.bstats[sg * 2 + 1];
+  float dzg[8], xhat[8], dx[8];
+  gn_bwd_terms8(a, b, n, h, w, c0, mean, rstd, dzg, xhat);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dx[j] = rstd * (dzg[j] - (m1 + xhat[j] * m2));
+  if (b.gres != nullptr) {
+    float r[8];
+    if (b.gres_at_input) load8(b.gres + ((static_cast<size_t>(n) * a.H + h) * a.W + w) * a.C + c0, r);
+    else gn_pull8(a, b.gres, n, h, w, c0, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dx[j] += r[j];
+  }
+  const size_t pix = (static_cast<size_t>(n) * a.H + h) * a.W + w;
+  float* gx; void* lo; int acc; size_t off;
+  if (c0 < a.C1) { gx = b.gx1; lo = b.gx1_lo; acc = b.acc1; off = pix * a.C1 + c0; }
+  else { gx = b.gx2; lo = b.gx2_lo; acc = b.acc2; off = pix * a.C2 + (c0 - a.C1); }
+  if (gx == nullptr && lo == nullptr) return;
+  if (acc && gx != nullptr) {
+    const float4* p = reinterpret_cast<const float4*>(gx + off);
+    const float4 u = p[0], v = p[1];
+    dx[0] += u.x; dx[1] += u.y; dx[2] += u.z; dx[3] += u.w;
+    dx[4] += v.x; dx[5] += v.y; dx[6] += v.z; dx[7] += v.w;
+  }
+  if (gx != nullptr) store8(gx, off, ISB_F32, dx);
+  if (lo != nullptr) store8(lo, off, b.lo_dtype, dx);
+}
+
+static int gn_fill_args(const isb_gn_desc* d, void* scratch, GnArgs* a) {
+  ISB_CHECK_ARG(d->x1 != nullptr && d->C1 > 0, "groupnorm: x1 missing");
+  ISB_CHECK_ARG(scratch != nullptr, "groupnorm: scratch missing");
+  a->x1 = d->x1; a->x2 = d->x2;
+  a->C1 = d->C1; a->C2 = d->x2 ? d->C2 : 0;
+  a->C = a->C1 + a->C2;
+  a->groups = d->groups;
+  ISB_CHECK_ARG(d->groups > 0 && a->C % d->groups == 0, "groupnorm: C=%d not divisible by groups=%d", a->C, d->groups);
+  a->Cg = a->C / d->groups;
+  ISB_CHECK_ARG(a->Cg % 8 == 0 && a->C1 % 8 == 0, "groupnorm: channels per group (%d) and C1 (%d) must be multiples of 8", a->Cg, a->C1);
+  a->N = d->N; a->H = d->H; a->W = d->W; a->HW = d->H * d->W;
+  ISB_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0, "groupnorm: bad N/H/W");
+  ISB_CHECK_ARG(d->resample >= 0 && d->resample <= 2, "groupnorm: bad resample");
+  ISB_CHECK_ARG(d->resample != 1 || (d->H % 2 == 0 && d->W % 2 == 0), "groupnorm: avg-pool needs even H,W");
+  a->eps = d->eps;
+  a->gamma = d->gamma; a->beta = d->beta;
+  ISB_CHECK_ARG(d->gamma && d->beta && d->stats, "groupnorm: gamma/beta/stats missing");
+  a->film = d->film; a->film_stride = d->film_stride;
+  ISB_CHECK_ARG(d->film == nullptr || d->film_stride >= 2 * a->C, "groupnorm: film_stride too small");
+  a->silu = d->silu; a->resample = d->resample;
+  a->stats = d->stats;
+  const size_t ng = static_cast<size_t>(d->N) * d->groups;
+  char* s = static_cast<char*>(scratch);
+  a->counters = reinterpret_cast<int*>(s);
+  size_t off = (ng * sizeof(int) + 15) & ~static_cast<size_t>(15);
+  a->partials = reinterpret_cast<double2*>(s + off);
+  off += ng * GN_MAX_SPLITS * sizeof(double2);
+  a->bstats = reinterpret_cast<float*>(s + off);
+  const long long vec = static_cast<long long>(a->HW) * (a->Cg / 8);
+  long long splits = (4LL * num_sms()) / static_cast<long long>(ng);
+  const long long by_work = vec / 512;
+  if (splits > by_work) splits = by_work;
+  if (splits > GN_MAX_SPLITS) splits = GN_MAX_SPLITS;
+  if (splits < 1) splits = 1;
+  a->splits = static_cast<int>(splits);
+  return ISB_OK;
+}
+
+}  // namespace isb
+
+extern "C" {
+
+size_t isb_gn_scratch_bytes(int N, int groups) {
+  const size_t ng = static_cast<size_t>(N) * groups;
+  size_t off = (ng * sizeof(int) + 15) & ~static_cast<size_t>(15);
+  off += ng * isb::GN_MAX_SPLITS * sizeof(double2);
+  off += ng * 2 * sizeof(float);
+  return off;
+}
+
+int isb_gn_forward(const isb_gn_desc* d, void* scratch, isb_stream_t stream) {
+  ISB_CHECK_ARG(d != nullptr, "isb_gn_forward: null desc");
+  isb::GnArgs a;
+  int rc = isb::gn_fill_args(d, scratch, &a);
+  if (rc) return rc;
+  ISB_CHECK_ARG(d->y != nullptr, "isb_gn_forward: y missing");
+  cudaStream_t st = isb::as_stream(stream);
+  isb::gn_stats_kernel<<<dim3(a.splits, a.groups, a.N), 256, 0, st>>>(a);
+  ISB_LAUNCH_CHECK();
+  isb::GnFwdOut o{d->y, d->y_dtype, d->raw, d->raw_dtype, d->xres};
+  const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;
+  const long long total = static_cast<long long>(a.N) * Ho * Wo * (a.C / 8);
+  isb::gn_apply_kernel<<<isb::cdiv(total, 256), 256, 0, st>>>(a, o);
+  ISB_LAUNCH_CHECK();
+  return ISB_OK;
+}
+
+int isb_gn_backward(const isb_gn_bwd_desc* d, void* scratch, isb_stream_t stream) {
+  ISB_CHECK_ARG(d != nullptr && d->dy != nullptr, "isb_gn_backward: dy missing");
+  isb::GnArgs a;
+  int rc = isb::gn_fill_args(&d->f, scratch, &a);
+  if (rc) return rc;
+  ISB_CHECK_ARG(d->gx1 != nullptr || d->gx2 != nullptr || d->gx1_lo != nullptr || d->gx2_lo != nullptr,
+                "isb_gn_backward: no gradient output");
+  isb::GnBwdArgs b{d->dy, d->gres, d->gres_at_input, d->gx1, d->acc1, d->gx1_lo,
+                   d->gx2, d->acc2, d->gx2_lo, d->lo_dtype};
+  cudaStream_t st = isb::as_stream(stream);
+  isb::gn_bwd_reduce_kernel<<<dim3(a.splits, a.groups, a.N), 256, 0, st>>>(a, b);
+  ISB_LAUNCH_CHECK();
+  const long long total = static_cast<long long>(a.N) * a.HW * (a.C / 8);
+  isb::gn_bwd_apply_kernel<<<isb::cdiv(total, 256), 256, 0, st>>>(a, b);
+  ISB_LAUNCH_CHECK();
+  return ISB_OK;
+}
+
+}  // extern "C"

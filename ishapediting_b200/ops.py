@@ -1,0 +1,268 @@
+"""Operator layer: torch CUDA tensors in, C-ABI calls on torch's current stream out.
+
+Everything is NHWC and preallocated by the caller (the UNet plan); PyTorch is used only for
+device memory and streams.  `CudaOps` is the only backend the product ships — the pure-torch
+mirror of this interface used to validate the graph logic on CPU lives under tests/ and is never
+imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype=None):
+    assert t.is_cuda and t.is_contiguous(), "ops expect contiguous CUDA tensors"
+    if dtype is not None:
+        assert t.dtype == dtype, f"expected {dtype}, got {t.dtype}"
+    return t
+
+
+class CudaOps:
+    name = "cuda"
+
+    def __init__(self, device=None, mode: str = "bf16"):
+        if not torch.cuda.is_available():
+            raise _lib.IsbError("ishapediting_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        assert mode in ("bf16", "fp32")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.mode = mode
+        self.lo = torch.bfloat16 if mode == "bf16" else torch.float32
+        self.lib = _lib.init(self.device.index or 0)
+        self._ws = None
+        self._gn_scratch = None
+        self._gn_scratch_n = 0
+
+    # ---- memory -----------------------------------------------------------
+    def empty(self, shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype=torch.float32):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def _workspace(self, nbytes):
+        if nbytes == 0:
+            return None, 0
+        if self._ws is None or self._ws.numel() < nbytes:
+            if torch.cuda.is_current_stream_capturing():
+                raise _lib.IsbError("conv workspace must be sized by an eager warm-up before graph capture")
+            self._ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+        return self._ws, self._ws.numel()
+
+    def _scratch(self, N, groups=32):
+        need = N * groups
+        if self._gn_scratch is None or self._gn_scratch_n < need:
+            nbytes = self.lib.isb_gn_scratch_bytes(N, groups)
+            self._gn_scratch = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            self._gn_scratch_n = need
+        return self._gn_scratch
+
+    # ---- layout -------------------------------------------------------------
+    def to_nhwc(self, x_nchw, out):
+        N, Cc, H, W = x_nchw.shape
+        _chk(x_nchw, torch.float32); _chk(out)
+        assert out.shape[0] == N and out.shape[1] == H and out.shape[2] == W
+        _lib.check(self.lib.isb_nchw_to_nhwc(_p(x_nchw), _p(out), _DT[out.dtype], N, Cc, H, W, out.shape[3], _stream()),
+                   "isb_nchw_to_nhwc")
+        return out
+
+    def to_nchw(self, x_nhwc, out_nchw):
+        N, Cc, H, W = out_nchw.shape
+        _chk(x_nhwc); _chk(out_nchw, torch.float32)
+        _lib.check(self.lib.isb_nhwc_to_nchw(_p(x_nhwc), _DT[x_nhwc.dtype], _p(out_nchw), N, Cc, H, W,
+                                             x_nhwc.shape[3], _stream()), "isb_nhwc_to_nchw")
+        return out_nchw
+
+    def cast_lo(self, src, dst):
+        _chk(src, torch.float32); _chk(dst)
+        if dst.dtype == torch.float32:
+            dst.copy_(src)
+        else:
+            _lib.check(self.lib.isb_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), "isb_cast_f32_bf16")
+        return dst
+
+    # ---- conv / linear --------------------------------------------------------
+    def conv(self, a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None):
+        """a [N,H,W,Cin], w packed [Cout, k*k*Cin (+Cin2)], out [N,H,W,Cout]."""
+        _chk(a); _chk(w, a.dtype); _chk(out)
+        N, H, W, Cin = a.shape
+        d = _lib.ConvDesc()
+        d.a, d.a_dtype = _p(a), _DT[a.dtype]
+        d.N, d.H, d.W, d.Cin, d.ksize = N, H, W, Cin, ksize
+        if a2 is not None:
+            _chk(a2, a.dtype)
+            assert a2.shape[:3] == a.shape[:3]
+            d.a2, d.Cin2 = _p(a2), a2.shape[3]
+        d.w = _p(w)
+        d.bias = _p(_chk(bias, torch.float32)) if bias is not None else None
+        if residual is not None:
+            _chk(residual, torch.float32)
+            assert residual.shape == out.shape
+            d.residual = _p(residual)
+        d.out, d.out_dtype, d.Cout = _p(out), _DT[out.dtype], out.shape[3]
+        assert w.shape[0] == d.Cout and w.shape[1] == ksize * ksize * Cin + (a2.shape[3] if a2 is not None else 0), \
+            f"packed weight {tuple(w.shape)} does not match conv {Cin}->{d.Cout} k{ksize}"
+        d.accumulate = int(accumulate)
+        if tune:
+            d.block_n, d.split_k, d.stages = tune.get("block_n", 0), tune.get("split_k", 0), tune.get("stages", 0)
+        ws, ws_bytes = self._workspace(self.lib.isb_conv2d_workspace(C.byref(d)))
+        _lib.check(self.lib.isb_conv2d(C.byref(d), _p(ws), ws_bytes, _stream()), "isb_conv2d")
+        return out
+
+    # ---- group norm -------------------------------------------------------------
+    def _gn_desc(self, x1, x2, gamma, beta, film, film_off, silu, resample, stats):
+        d = _lib.GnDesc()
+        _chk(x1, torch.float32)
+        N, H, W, C1 = x1.shape
+        d.x1, d.C1 = _p(x1), C1
+        if x2 is not None:
+            _chk(x2, torch.float32)
+            assert x2.shape[:3] == x1.shape[:3]
+            d.x2, d.C2 = _p(x2), x2.shape[3]
+        d.N, d.H, d.W = N, H, W
+        d.groups, d.eps = 32, 1e-5
+        d.gamma, d.beta = _p(_chk(gamma, torch.float32)), _p(_chk(beta, torch.float32))
+        if film is not None:
+            _chk(film, torch.float32)
+            d.film = C.c_void_p(film.data_ptr() + 4 * film_off)
+            d.film_stride = film.shape[1]
+        d.silu, d.resample = int(silu), int(resample)
+        d.stats = _p(_chk(stats, torch.float32))
+        return d
+
+    def gn_forward(self, x1, x2, gamma, beta, film, film_off, silu, resample, stats, y, raw=None, xres=None):
+        d = self._gn_desc(x1, x2, gamma, beta, film, film_off, silu, resample, stats)
+        d.y, d.y_dtype = _p(_chk(y)), _DT[y.dtype]
+        if raw is not None:
+            d.raw, d.raw_dtype = _p(_chk(raw)), _DT[raw.dtype]
+        if xres is not None:
+            d.xres = _p(_chk(xres, torch.float32))
+        _lib.check(self.lib.isb_gn_forward(C.byref(d), _p(self._scratch(x1.shape[0])), _stream()), "isb_gn_forward")
+        return y
+
+    def gn_backward(self, x1, x2, gamma, beta, film, film_off, silu, resample, stats, dy, gres, gres_at_input,
+                    gx1, acc1, gx1_lo, gx2, acc2, gx2_lo):
+        b = _lib.GnBwdDesc()
+        b.f = self._gn_desc(x1, x2, gamma, beta, film, film_off, silu, resample, stats)
+        b.dy = _p(_chk(dy, torch.float32))
+        if gres is not None:
+            b.gres, b.gres_at_input = _p(_chk(gres, torch.float32)), int(gres_at_input)
+        lo_dtype = None
+        if gx1 is not None:
+            b.gx1, b.acc1 = _p(_chk(gx1, torch.float32)), int(acc1)
+        if gx1_lo is not None:
+            b.gx1_lo, lo_dtype = _p(_chk(gx1_lo)), gx1_lo.dtype
+        if gx2 is not None:
+            b.gx2, b.acc2 = _p(_chk(gx2, torch.float32)), int(acc2)
+        if gx2_lo is not None:
+            assert lo_dtype is None or lo_dtype == gx2_lo.dtype
+            b.gx2_lo, lo_dtype = _p(_chk(gx2_lo)), gx2_lo.dtype
+        b.lo_dtype = _DT[lo_dtype] if lo_dtype is not None else F32
+        _lib.check(self.lib.isb_gn_backward(C.byref(b), _p(self._scratch(x1.shape[0])), _stream()), "isb_gn_backward")
+
+    # ---- attention ----------------------------------------------------------------
+    def attention_forward(self, qkv, heads, probs, out):
+        _chk(qkv, torch.float32); _chk(probs, torch.float32); _chk(out)
+        N, H, W, C3 = qkv.shape
+        T, ch = H * W, C3 // (3 * heads)
+        _lib.check(self.lib.isb_attention_forward(_p(qkv), N, T, heads, ch, _p(probs), _p(out), _DT[out.dtype],
+                                                  _stream()), "isb_attention_forward")
+        return out
+
+    def attention_backward(self, qkv, probs, d_out, heads, tmp, d_qkv):
+        _chk(qkv, torch.float32); _chk(probs, torch.float32); _chk(d_out, torch.float32); _chk(tmp, torch.float32)
+        _chk(d_qkv)
+        N, H, W, C3 = qkv.shape
+        T, ch = H * W, C3 // (3 * heads)
+        _lib.check(self.lib.isb_attention_backward(_p(qkv), _p(probs), _p(d_out), N, T, heads, ch, _p(tmp), _p(d_qkv),
+                                                   _DT[d_qkv.dtype], _stream()), "isb_attention_backward")
+        return d_qkv
+
+    # ---- timestep embedding ---------------------------------------------------------
+    def time_embed(self, t, freqs, w1, b1, w2, b2, w_all, b_all, scratch, film_all):
+        _chk(t, torch.int64)
+        N = t.shape[0]
+        model_ch, hidden = w1.shape[1], w1.shape[0]
+        assert scratch.numel() >= N * (model_ch + 2 * hidden)
+        _lib.check(self.lib.isb_time_embed(_p(t), _p(freqs), N, model_ch, hidden, _p(w1), _p(b1), _p(w2), _p(b2),
+                                           _p(w_all), _p(b_all), w_all.shape[0], _p(scratch), _p(film_all), _stream()),
+                   "isb_time_embed")
+        return film_all
+
+    # ---- DDPM update -------------------------------------------------------------------
+    def ddpm_step(self, x, model_out, coef, clip_denoised, noise=None, grad=None, x_next=None, sample=None, mean=None,
+                  var=None, x0=None, eps=None):
+        _chk(x, torch.float32); _chk(model_out, torch.float32); _chk(coef, torch.float32)
+        N, Cc, H, W = x.shape
+        d = _lib.DdpmDesc()
+        d.x, d.model_out, d.model_out_cstride = _p(x), _p(model_out), model_out.shape[3]
+        d.noise, d.grad, d.coef = _p(noise), _p(grad), _p(coef)
+        d.N, d.C, d.H, d.W, d.clip_denoised = N, Cc, H, W, int(clip_denoised)
+        d.x_next, d.sample, d.mean, d.var, d.x0, d.eps = _p(x_next), _p(sample), _p(mean), _p(var), _p(x0), _p(eps)
+        _lib.check(self.lib.isb_ddpm_step(C.byref(d), _stream()), "isb_ddpm_step")
+
+    # ---- drag guidance --------------------------------------------------------------------
+    def resize_feat_align(self, feat, chan_map, out):
+        _chk(feat, torch.float32); _chk(chan_map, torch.int32); _chk(out, torch.float32)
+        S, Cf, Ca = feat.shape[1], feat.shape[3], out.shape[3]
+        _lib.check(self.lib.isb_resize_feat_align(_p(feat), S, Cf, _p(chan_map), _p(out), Ca, _stream()),
+                   "isb_resize_feat_align")
+        return out
+
+    def drag_partial_len(self, S, Cf, npts):
+        return int(self.lib.isb_drag_partial_len(S, Cf, npts))
+
+    def drag_loss_grad(self, feat, origin, chan_map, inv_map, patch_xy, shift_xy, weight, group_size, bbox, mask,
+                       mask_count, inv_count, cof, loss_type, g, pt_info, partial, loss, d_feat):
+        d = _lib.DragDesc()
+        _chk(feat, torch.float32); _chk(origin, torch.float32); _chk(d_feat, torch.float32)
+        d.feat, d.S, d.Cf = _p(feat), feat.shape[1], feat.shape[3]
+        d.origin, d.Ca = _p(origin), origin.shape[3]
+        d.chan_map, d.inv_map = _p(_chk(chan_map, torch.int32)), _p(_chk(inv_map, torch.int32))
+        d.patch_xy, d.shift_xy, d.weight = _p(_chk(patch_xy, torch.float32)), _p(_chk(shift_xy, torch.float32)), \
+            _p(_chk(weight, torch.float32))
+        d.npts, d.group_size = patch_xy.shape[1], group_size
+        d.bbox = _p(_chk(bbox, torch.int32))
+        d.mask, d.mask_count = (_p(_chk(mask, torch.uint8)) if mask is not None else None), int(mask_count)
+        d.inv_count, d.cof, d.loss_type = float(inv_count), float(cof), int(loss_type)
+        d.g, d.pt_info = _p(_chk(g, torch.float32)), _p(_chk(pt_info, torch.float32))
+        d.partial, d.partial_len = _p(_chk(partial, torch.float64)), partial.numel()
+        d.loss, d.d_feat = _p(_chk(loss, torch.float32)), _p(d_feat)
+        _lib.check(self.lib.isb_drag_loss_grad(C.byref(d), _stream()), "isb_drag_loss_grad")
+
+    # ---- triplane decoder ---------------------------------------------------------------------
+    @staticmethod
+    def _mlp(weights):
+        m = _lib.TriplaneMlp()
+        m.fourier_B, m.w1, m.b1, m.w2, m.b2, m.w3, m.b3 = (_p(_chk(w, torch.float32)) for w in weights)
+        return m
+
+    def decode_grid(self, planes_hwc, weights, lin, x_begin, x_end, out):
+        _chk(planes_hwc, torch.float32); _chk(lin, torch.float32); _chk(out, torch.float32)
+        m = self._mlp(weights)
+        _lib.check(self.lib.isb_triplane_decode_grid(_p(planes_hwc), planes_hwc.shape[1], C.byref(m), _p(lin),
+                                                     lin.numel(), x_begin, x_end, _p(out), _stream()),
+                   "isb_triplane_decode_grid")
+        return out
+
+    def decode_points(self, planes_hwc, weights, coords, out):
+        _chk(planes_hwc, torch.float32); _chk(coords, torch.float32); _chk(out, torch.float32)
+        m = self._mlp(weights)
+        _lib.check(self.lib.isb_triplane_decode_points(_p(planes_hwc), planes_hwc.shape[1], C.byref(m), _p(coords),
+                                                       coords.shape[0], _p(out), _stream()),
+                   "isb_triplane_decode_points")
+        return out
