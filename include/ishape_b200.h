@@ -190,6 +190,7 @@ enum isb_sched_coef {
 };
 typedef struct isb_ddpm_desc {
   const float* x; const float* model_out; int model_out_cstride;
+  int model_out_nchw;   /* 1: model_out is NCHW [N,2C,H,W] (generic API route) */
   const float* noise; const float* grad;
   const float* coef;  /* device [8] */
   int N, C, H, W; int clip_denoised;

@@ -64,7 +64,7 @@ class GnBwdDesc(C.Structure):
 
 class DdpmDesc(C.Structure):
     _fields_ = [
-        ("x", c_void_p), ("model_out", c_void_p), ("model_out_cstride", c_int),
+        ("x", c_void_p), ("model_out", c_void_p), ("model_out_cstride", c_int), ("model_out_nchw", c_int),
         ("noise", c_void_p), ("grad", c_void_p), ("coef", c_void_p),
         ("N", c_int), ("C", c_int), ("H", c_int), ("W", c_int), ("clip_denoised", c_int),
         ("x_next", c_void_p), ("sample", c_void_p), ("mean", c_void_p), ("var", c_void_p),

@@ -11,7 +11,7 @@
 namespace isb {
 
 struct DdpmArgs {
-  const float* x; const float* mo; int cstride;
+  const float* x; const float* mo; int cstride; int mo_nchw;
   const float* noise; const float* grad; const float* coef;
   int C, HW; int clip;
   float* x_next; float* sample; float* mean; float* var; float* x0; float* eps;
@@ -29,7 +29,7 @@ ddpm_step_kernel(const DdpmArgs a) {
   for (int i = 0; i < 4; ++i) {
     const int p = p0 + ty + i * 8, c = c0 + tx;
     float e = 0.f, v = 0.f;
-    if (p < a.HW && c < a.C) {
+    if (!a.mo_nchw && p < a.HW && c < a.C) {
       const float* src = a.mo + (static_cast<size_t>(n) * a.HW + p) * a.cstride;
       e = __ldg(src + c);
       v = __ldg(src + a.C + c);
@@ -47,7 +47,11 @@ ddpm_step_kernel(const DdpmArgs a) {
     const int c = c0 + ty + i * 8, p = p0 + tx;
     if (c >= a.C || p >= a.HW) continue;
     const size_t off = (static_cast<size_t>(n) * a.C + c) * a.HW + p;
-    const float e = t_eps[tx][ty + i * 8], v = t_v[tx][ty + i * 8];
+    float e = t_eps[tx][ty + i * 8], v = t_v[tx][ty + i * 8];
+    if (a.mo_nchw) {  // model output still in the reference's NCHW layout (generic API route)
+      e = __ldg(a.mo + (static_cast<size_t>(n) * 2 * a.C + c) * a.HW + p);
+      v = __ldg(a.mo + (static_cast<size_t>(n) * 2 * a.C + a.C + c) * a.HW + p);
+    }
     const float xv = __ldg(a.x + off);
     // learned-range variance (gaussian_diffusion.py:275-279)
     const float frac = (v + 1.0f) / 2.0f;
@@ -76,8 +80,8 @@ extern "C" {
 
 int isb_ddpm_step(const isb_ddpm_desc* d, isb_stream_t stream) {
   ISB_CHECK_ARG(d && d->x && d->model_out && d->coef, "isb_ddpm_step: null pointer");
-  ISB_CHECK_ARG(d->N > 0 && d->C > 0 && d->H > 0 && d->W > 0 && d->model_out_cstride >= 2 * d->C, "isb_ddpm_step: bad shape");
-  isb::DdpmArgs a{d->x, d->model_out, d->model_out_cstride, d->noise, d->grad, d->coef,
+  ISB_CHECK_ARG(d->N > 0 && d->C > 0 && d->H > 0 && d->W > 0 && (d->model_out_nchw || d->model_out_cstride >= 2 * d->C), "isb_ddpm_step: bad shape");
+  isb::DdpmArgs a{d->x, d->model_out, d->model_out_cstride, d->model_out_nchw, d->noise, d->grad, d->coef,
                   d->C, d->H * d->W, d->clip_denoised,
                   d->x_next, d->sample, d->mean, d->var, d->x0, d->eps};
   dim3 grid(isb::cdiv(a.HW, 32), isb::cdiv(a.C, 32), d->N);

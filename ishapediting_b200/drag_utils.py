@@ -1,0 +1,423 @@
+"""Drag editing logic with the reference's surface (/root/reference/drag_utils.py).
+
+Kept: get_args (:23-58), make_offsets (:134-138), resize_feat_align (:141-159), DragStuff with
+update_latent_params (:252-280), get_mesh (:282-300), training (:302-399, a generator yielding
+progress), latent_inversion (:552-566), clear_params / reset_params / set_offset1 and the attributes
+the GUI reads (w, w0, feature_guidance, variance, variance_noise, train_flag, r1, offset1,
+voxel_size).  Out of scope here: checkpoint discovery on disk (update_model_params :210-250 — weights
+are loaded with load_state_dict), train_triplane (:401-471), Open3D meshing.
+
+What differs from the reference, by design:
+  * the guided step never enters torch.autograd: UNet forward plan -> isb_drag_loss_grad -> UNet
+    input-gradient plan -> isb_ddpm_step, all on one stream, optionally replayed as one CUDA graph;
+  * only the input gradient is computed (the reference also computes and accumulates weight
+    gradients for 406 tensors, :383, and never reads them);
+  * the feature cache stays on the device (the reference moves 8.4 MB per step to and from the CPU,
+    :276,352);
+  * the mask index sets (:322-334) are built with vectorised integer ops instead of Python sets —
+    same sets, checked bit-exactly in tests.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+from argparse import Namespace
+
+import numpy as np
+import torch as th
+import torch.nn.functional as F
+
+from .guided_diffusion.script_util import args_to_dict, create_model_and_diffusion, model_and_diffusion_defaults
+from .triplane_decoder.axisnetworks import MultiTriplane
+from .triplane_decoder.visualize import create_obj_o3d, query_volume
+
+
+def get_args(argv=None):
+    """Reference :23-58.  Unlike the reference this does not parse sys.argv at import time; pass argv
+    explicitly (None -> defaults)."""
+    parser = argparse.ArgumentParser(description="Generate a set of triplane and their corresponding meshes")
+    parser.add_argument("--resolution", type=int, default=128)
+    parser.add_argument("--num_steps", type=int, default=200)
+    parser.add_argument("--shape_resolution", type=int, default=256)
+    parser.add_argument("--w_time", type=int, default=170)
+    parser.add_argument("--feat_layer", type=int, default=8)
+    parser.add_argument("--loss_type", type=str, default="l2")
+    parser.add_argument("--points_size", type=int, default=200000)
+    parser.add_argument("--points_uniform_ratio", type=float, default=0.5)
+    args = parser.parse_args([] if argv is None else argv)
+    return Namespace(
+        clip_denoised=True, num_samples=1, batch_size=1, use_ddim=False, model_path=None, stats_dir=None,
+        num_steps=args.num_steps, explicit_normalization=True, save_dir=None, save_intermediate=False,
+        save_timestep_interval=20, image_size=args.resolution, num_channels=256, num_res_blocks=2, num_heads=4,
+        num_heads_upsample=-1, num_head_channels=64, attention_resolutions="32,16,8", channel_mult="", dropout=0.1,
+        class_cond=False, shape_resolution=args.shape_resolution, use_checkpoint=False, use_scale_shift_norm=True,
+        resblock_updown=True, use_fp16=True, use_new_attention_order=False, in_out_channels=96, learn_sigma=True,
+        diffusion_steps=1000, noise_schedule="linear", timestep_respacing=str(args.num_steps), w_time=args.w_time,
+        feat_layer=args.feat_layer, points_size=args.points_size, points_uniform_ratio=args.points_uniform_ratio,
+        loss_type=args.loss_type, use_kl=False, predict_xstart=False, rescale_timesteps=False, decoder_ckpt=None,
+        rescale_learned_sigmas=False)
+
+
+def make_offsets(r, device):
+    p = th.arange(-r, r + 1, device=device)
+    px, py, pz = th.meshgrid(p, p, p, indexing="ij")
+    return th.stack([px.reshape(-1), py.reshape(-1), pz.reshape(-1)], dim=-1)
+
+
+# ------------------------------------------------------------------------------------------------------
+# resize_feat_align as an index map
+# ------------------------------------------------------------------------------------------------------
+def align_maps(channel_num):
+    """Index maps equivalent to resize_feat_align(cat_var=True) (reference :141-159) for a feature with
+    `channel_num` channels: returns (chan_map int32 [3*Ca], inv_map int32 [channel_num], Ca) where
+    aligned[pl, a] = feature[chan_map[pl*Ca + a]] and inv_map is its inverse (-1 = dropped channel).
+    The nearest-neighbour channel resampling is taken from F.interpolate itself, so the index rule is
+    torch's, not a re-derivation."""
+    assert channel_num % 2 == 0
+    half = channel_num // 2
+    expect = half - half % 3
+    if half % 3:
+        idx = th.arange(half, dtype=th.float32).reshape(1, 1, 1, half)
+        src = F.interpolate(idx, (1, expect)).reshape(-1).long()      # nearest, as reference :149-151
+    else:
+        src = th.arange(half)
+    per = expect // 3
+    Ca = 2 * per
+    chan_map = th.empty(3, Ca, dtype=th.int64)
+    for pl in range(3):
+        chan_map[pl, :per] = src[pl * per:(pl + 1) * per]              # mean half reshaped to (3, per, H, W)
+        chan_map[pl, per:] = half + src[pl * per:(pl + 1) * per]       # var half
+    inv = th.full((channel_num,), -1, dtype=th.int64)
+    inv[chan_map.reshape(-1)] = th.arange(3 * Ca)
+    return chan_map.reshape(-1).to(th.int32), inv.to(th.int32), Ca
+
+
+def resize_feat_align(feature, cat_var=True):
+    """Reference :141-159: (1, C, H, W) -> (3, Ca, H, W) fp32.  Gather kernel on the device."""
+    assert cat_var, "cat_var=False is never used by the editor"
+    b, c, h, w = feature.shape
+    assert b == 1 and h == w
+    from .ops import CudaOps
+    ops = CudaOps(feature.device, "fp32")
+    chan_map, _, Ca = align_maps(c)
+    nhwc = ops.to_nhwc(feature.detach().to(th.float32).contiguous(), ops.empty((1, h, w, c)))
+    out = ops.resize_feat_align(nhwc, chan_map.to(feature.device), ops.empty((3, h, w, Ca)))
+    return out.permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------------
+# geometry of one edit (host side, once per training() call)
+# ------------------------------------------------------------------------------------------------------
+class DragGeometry:
+    """Everything training() derives from (sources, targets) before its loop (reference :305-334).
+
+    The (2r+1)^3 patch lattice around a handle projects, on each of the three planes, onto a
+    (2r+1)^2 lattice of distinct 2-D points, each hit (2r+1) times with identical coordinates (the
+    projected-out offset does not enter).  Only the distinct points are kept, with that multiplicity.
+    """
+
+    def __init__(self, sources, targets, r, voxel_size, S, Ca):
+        src = th.as_tensor(np.asarray(sources), dtype=th.float32).reshape(-1, 3)
+        tgt = th.as_tensor(np.asarray(targets), dtype=th.float32).reshape(-1, 3)
+        assert src.shape == tgt.shape
+        B = src.shape[0]
+        side = 2 * r + 1
+        off1d = voxel_size * th.arange(-r, r + 1)            # int64 * python float -> fp32, as :316-317
+        axes = ((0, 1), (1, 2), (0, 2))                      # plane grids: xy, yz, xz (:318-321)
+        self.group_size = side * side
+        self.npts = B * self.group_size
+
+        def plane_pts(p):
+            out = th.empty(3, B, side, side, 2)
+            for pl, (au, av) in enumerate(axes):
+                u = p[:, au, None] + off1d[None, :]          # [B, side] -> W coordinate
+                v = p[:, av, None] + off1d[None, :]          # [B, side] -> H coordinate
+                out[pl, ..., 0] = u[:, :, None]
+                out[pl, ..., 1] = v[:, None, :]
+            return out.reshape(3, self.npts, 2).contiguous()
+
+        self.patch_xy = plane_pts(src)
+        self.shift_xy = plane_pts(tgt)
+        self.weight = th.full((self.npts,), float(side))
+        self.inv_count = 1.0 / (3.0 * Ca * B * side ** 3)
+        # conservative bounding boxes (floor index of the shift samples, padded by one pixel)
+        ix = th.floor(((self.shift_xy + 1.0) / 2.0) * (S - 1)).to(th.int64).reshape(3, B, self.group_size, 2)
+        self.bbox = th.stack([ix[..., 0].amin(-1) - 1, ix[..., 0].amax(-1) + 1,
+                              ix[..., 1].amin(-1) - 1, ix[..., 1].amax(-1) + 1], dim=-1).to(th.int32).contiguous()
+        # mask regulariser: complement of the rounded content pixels (:322-334), [plane, row, col]
+        content = th.zeros(3, S, S, dtype=th.bool)
+        for pts in (self.patch_xy, self.shift_xy):
+            rc = th.round((pts + 1) * (S - 1) / 2).to(th.int16).long()   # [..., 0] = col (W), [..., 1] = row (H)
+            for pl in range(3):
+                col, row = rc[pl, :, 0], rc[pl, :, 1]
+                ok = (col >= 0) & (col < S) & (row >= 0) & (row < S)
+                content[pl, row[ok], col[ok]] = True
+        self.mask = (~content).to(th.uint8).contiguous()
+        self.mask_count = int(self.mask.sum())
+
+    def mask_index_sets(self):
+        """The three (K,2) [row, col] index lists the reference builds (order-insensitive)."""
+        return [th.nonzero(self.mask[pl].bool()) for pl in range(3)]
+
+    def to(self, device):
+        g = copy.copy(self)
+        for k in ("patch_xy", "shift_xy", "weight", "bbox", "mask"):
+            setattr(g, k, getattr(self, k).to(device))
+        return g
+
+
+# ------------------------------------------------------------------------------------------------------
+# the guided step (fast path)
+# ------------------------------------------------------------------------------------------------------
+class GuidedStepper:
+    """One drag-guided DDPM step = UNet forward + drag loss/grad + UNet dgrad + fused update, issued
+    as C-ABI calls on the current stream (reference loop body :340-392).  With `use_graph` the whole
+    sequence is captured once and replayed; per-step inputs (step scalars, timestep, origin feature,
+    noise) are refreshed in static device buffers before each replay."""
+
+    def __init__(self, model, diffusion, geometry: DragGeometry, feat_layer, cof, loss_type, scale,
+                 clip_denoised=True, use_graph=True):
+        self.model, self.diffusion = model, diffusion
+        self.plan = model.plan(1, model.image_size, model.image_size, want_backward=True)
+        ops = self.ops = self.plan.ops
+        dev = ops.device
+        self.geo = geometry.to(dev)
+        self.feat_layer, self.cof, self.scale, self.clip = feat_layer, float(cof), float(scale), clip_denoised
+        self.loss_type = 1 if loss_type == "l1" else 0
+        inter = self.plan.block_out[feat_layer]
+        _, S, _, Cf = inter.val.shape
+        chan_map, inv_map, Ca = align_maps(Cf)
+        self.chan_map, self.inv_map, self.S, self.Cf, self.Ca = chan_map.to(dev), inv_map.to(dev), S, Cf, Ca
+        C, R = model.in_channels, model.image_size
+        self.img = ops.empty((1, C, R, R))
+        self.img_next = ops.empty((1, C, R, R))
+        self.noise = ops.empty((1, C, R, R))
+        self.grad = ops.empty((1, C, R, R))
+        self.variance = ops.empty((1, C, R, R))
+        self.sample = ops.empty((1, C, R, R))
+        self.origin = ops.empty((3, S, S, Ca))
+        self.coef = ops.empty((8,))
+        self.coef_table = diffusion.coef_table(dev, guide_scale=self.scale)
+        tmap = getattr(diffusion, "timestep_map", list(range(diffusion.num_timesteps)))
+        self.t_table = th.tensor(tmap, device=dev, dtype=th.int64)
+        npts = self.geo.npts
+        self.g = ops.empty((3, npts, Ca))
+        self.pt_info = ops.empty((3, npts, 4))
+        self.partial = ops.zeros((ops.drag_partial_len(S, Cf, npts),), th.float64)
+        self.loss = ops.zeros((1,))
+        self.plan.ensure_grad(inter)
+        self.use_graph = use_graph and dev.type == "cuda"
+        self._graph = None
+        self._warm = 0
+
+    def _body(self):
+        plan, ops, geo = self.plan, self.ops, self.geo
+        inter = plan.forward(self.img, plan.t_dev, self.feat_layer)
+        ops.drag_loss_grad(inter.val, self.origin, self.chan_map, self.inv_map, geo.patch_xy, geo.shift_xy,
+                           geo.weight, geo.group_size, geo.bbox, geo.mask, geo.mask_count, geo.inv_count,
+                           self.cof, self.loss_type, self.g, self.pt_info, self.partial, self.loss, inter.grad)
+        plan.begin_backward()
+        plan.seed_grad(inter)
+        plan.backward(self.grad)
+        ops.ddpm_step(self.img, plan.out_nhwc, self.coef, self.clip, noise=self.noise, grad=self.grad,
+                      x_next=self.img_next, sample=self.sample, var=self.variance)
+        self.img.copy_(self.img_next)
+
+    def step(self, i, origin_feature, noise=None):
+        """Advance self.img from respaced step i to i-1.  origin_feature: (3,S,S,Ca) device tensor."""
+        self.coef.copy_(self.coef_table[i])
+        self.plan.t_dev.copy_(self.t_table[i:i + 1])
+        self.origin.copy_(origin_feature)
+        if noise is None:
+            self.noise.normal_()
+        else:
+            self.noise.copy_(noise)
+        if not self.use_graph:
+            self._body()
+            return
+        if self._graph is None:
+            if self._warm < 1:          # eager warm-up sizes every workspace/scratch buffer
+                self._warm += 1
+                self._body()
+                return
+            img_keep = self.img.clone()
+            g = th.cuda.CUDAGraph()
+            with th.cuda.graph(g):
+                self._body()
+            self._graph = g
+            self.img.copy_(img_keep)    # capture does not execute; restore and replay for real
+        self._graph.replay()
+
+
+# ------------------------------------------------------------------------------------------------------
+# DragStuff
+# ------------------------------------------------------------------------------------------------------
+class DragStuff:
+    args = None   # set lazily: the reference parses sys.argv at class-definition time (:176)
+
+    def __init__(self, args=None, device=None, use_graph=True):
+        self.args = args if args is not None else (DragStuff.args or get_args())
+        self.device = th.device(device) if device is not None else th.device("cuda", th.cuda.current_device())
+        self.model, self.diffusion = create_model_and_diffusion(
+            **args_to_dict(self.args, model_and_diffusion_defaults().keys()))
+        self.model.to(self.device)
+        self.model.eval()
+        self.decoder = MultiTriplane(1, input_dim=3, output_dim=1).to(self.device)
+        self.decoder.eval()
+        self.range = 1.
+        self.middle = 0.
+        self.latent_code = None
+        self.w0 = None
+        self.w = None
+        self.r1 = 12
+        self.offset1 = make_offsets(self.r1, self.device)
+        self.voxel_size = 2. / self.args.shape_resolution
+        self.train_flag = True
+        self.targets = None
+        self.sources = None
+        self.mesh = None
+        self.mesh0 = None
+        self.noise = []
+        self.variance = []
+        self.variance_noise = []
+        self.feature_guidance = []       # device tensors, channels-last (3,S,S,Ca); see feature_guidance_nchw()
+        self.use_graph = use_graph
+        self.last_volume = None
+
+    def set_offset1(self, r1):
+        self.r1 = r1
+        self.offset1 = make_offsets(r1, self.device)
+
+    def feature_guidance_nchw(self, k):
+        """k-th cached feature in the reference's (3, Ca, S, S) layout."""
+        return self.feature_guidance[k].permute(0, 3, 1, 2)
+
+    # ---- no-grad trajectory + feature cache (reference :252-280) --------------------------------
+    def _nograd_step(self, plan, img, i, feat_layer, noise=None):
+        """One unguided step on the plan; returns (img_next, inter _T)."""
+        ops = plan.ops
+        dev = self.device
+        coef = self.diffusion.coef_table(dev)[i].contiguous()
+        tmap = self.diffusion.timestep_map_tensor(dev)
+        inter = plan.forward(img, tmap[i:i + 1].contiguous(), feat_layer)
+        nz = th.randn_like(img) if noise is None else noise
+        nxt = th.empty_like(img)
+        ops.ddpm_step(img, plan.out_nhwc, coef, self.args.clip_denoised, noise=nz, x_next=nxt)
+        return nxt, inter
+
+    def update_latent_params(self, img=None, **kwargs):
+        dev = self.device
+        R = self.args.image_size
+        if img is None:
+            img = th.randn((1, 96, R, R), device=dev)
+        elif th.is_tensor(img):
+            img = img.to(device=dev, dtype=th.float32)
+        elif isinstance(img, np.ndarray):
+            img = th.tensor(img, dtype=th.float32, device=dev)
+        else:
+            raise NotImplementedError("Unknown data type!")
+        self.latent_code = img.clone().detach()
+        plan = self.model.plan(1, R, R, want_backward=True)
+        chan_map = None
+        self.feature_guidance = []
+        with th.no_grad():
+            for i in range(self.args.num_steps - 1, -1, -1):
+                img, inter = self._nograd_step(plan, img.contiguous(), i, self.args.feat_layer, kwargs.get("noise"))
+                if i == self.args.w_time:
+                    self.w = img.clone().detach()
+                    self.w0 = self.w.clone().detach()
+                if i < self.args.w_time:
+                    if chan_map is None:
+                        cm, _, Ca = align_maps(inter.val.shape[3])
+                        chan_map = cm.to(dev)
+                    S = inter.val.shape[1]
+                    self.feature_guidance.append(plan.ops.resize_feat_align(inter.val, chan_map,
+                                                                            plan.ops.empty((3, S, S, Ca))))
+            assert len(self.feature_guidance) == self.args.w_time
+            self.mesh0 = self.get_mesh(tri_feat=img)
+            self.mesh = copy.deepcopy(self.mesh0) if not th.is_tensor(self.mesh0) else self.mesh0.clone()
+            return img
+
+    # ---- decode (reference :282-300) -----------------------------------------------------------------
+    def get_mesh(self, tri_feat=None, img=None, t=0):
+        R = self.args.image_size
+        with th.no_grad():
+            if tri_feat is None:
+                img = img if img is not None else th.randn((1, 96, R, R), device=self.device)
+                plan = self.model.plan(1, R, R, want_backward=True)
+                for i in range(t - 1, -1, -1):
+                    img, _ = self._nograd_step(plan, img.contiguous(), i, self.args.feat_layer)
+                tri_feat = img
+            tri_feat = (tri_feat * self.range + self.middle).reshape(3, 32, R, R)
+            for i in range(3):
+                self.decoder.embeddings[i] = tri_feat[[i]]
+            self.last_volume = query_volume(self.decoder, 0, res=self.args.shape_resolution)
+            mesh = create_obj_o3d(self.decoder, 0, res=self.args.shape_resolution) if _have_meshing() else self.last_volume
+            if hasattr(mesh, "filter_smooth_simple"):
+                return mesh.filter_smooth_simple(number_of_iterations=10)
+            return mesh
+
+    # ---- the guided edit (reference :302-399) -----------------------------------------------------------
+    def training(self, sources=None, targets=None, scale=600, cof=0.2, noises=None):
+        if self.args.num_samples > 1:
+            raise NotImplementedError("We can handle only one shape at each time!")
+        self.sources = th.tensor(np.asarray(sources), device=self.device, dtype=th.float32)
+        self.targets = th.tensor(np.asarray(targets), device=self.device, dtype=th.float32)
+        assert self.sources.shape[0] == self.targets.shape[0]
+        S, Ca = self.feature_guidance[0].shape[1], self.feature_guidance[0].shape[3]
+        geo = DragGeometry(np.asarray(sources), np.asarray(targets), self.r1, self.voxel_size, S, Ca)
+        stepper = GuidedStepper(self.model, self.diffusion, geo, self.args.feat_layer, cof, self.args.loss_type, scale,
+                                clip_denoised=True, use_graph=self.use_graph)
+        stepper.img.copy_(self.w.detach())
+        self.stepper = stepper
+        stop_time = 0
+        self.train_flag = True
+        w_time = self.args.w_time
+        for i in range(w_time - 1, -1, -1):
+            if not self.train_flag:
+                stop_time = i + 1
+                break
+            stepper.step(i, self.feature_guidance[w_time - 1 - i], None if noises is None else noises[w_time - 1 - i])
+            yield 1 - i / (w_time - 1.) if w_time > 1 else 1.0
+        self.mesh = self.get_mesh(img=stepper.img.clone(), t=stop_time)
+
+    # ---- real-shape inversion (reference :552-566) -----------------------------------------------------------
+    def latent_inversion(self, tri_feat):
+        with th.no_grad():
+            outs = self.diffusion.ddpm_inversion(self.model, tri_feat, self.args.w_time,
+                                                 clip_denoised=self.args.clip_denoised,
+                                                 feat_layer=self.args.feat_layer)
+            noise = outs["latent"]
+        self.w = noise.clone().detach()
+        self.w0 = self.w.clone().detach()
+        self.feature_guidance = [resize_feat_align(f).permute(0, 2, 3, 1).contiguous() for f in outs["inter_feat"]]
+        self.mesh = self.get_mesh(tri_feat=outs["sample"])
+        self.mesh0 = copy.deepcopy(self.mesh) if not th.is_tensor(self.mesh) else self.mesh.clone()
+        self.variance = [v.clone().detach() for v in outs["variance"]]
+        self.variance_noise = [v.clone().detach() for v in outs["variance_noise"]]
+
+    def clear_params(self):
+        self.mesh0 = None
+        self.mesh = None
+        self.latent_code = None
+        self.w0 = None
+        self.w = None
+        self.feature_guidance.clear()
+        self.noise.clear()
+        self.variance.clear()
+        self.variance_noise.clear()
+
+    def reset_params(self):
+        if self.mesh is not None:
+            self.mesh = copy.deepcopy(self.mesh0) if not th.is_tensor(self.mesh0) else self.mesh0.clone()
+        if self.w0 is not None:
+            self.w = self.w0.clone().detach()
+
+
+def _have_meshing():
+    try:
+        import mcubes  # noqa: F401
+        import open3d  # noqa: F401
+        return True
+    except ImportError:
+        return False

@@ -209,7 +209,11 @@ class CudaOps:
         _chk(x, torch.float32); _chk(model_out, torch.float32); _chk(coef, torch.float32)
         N, Cc, H, W = x.shape
         d = _lib.DdpmDesc()
-        d.x, d.model_out, d.model_out_cstride = _p(x), _p(model_out), model_out.shape[3]
+        d.x, d.model_out = _p(x), _p(model_out)
+        if model_out.shape[1] == 2 * Cc and model_out.shape[2:] == x.shape[2:]:
+            d.model_out_nchw, d.model_out_cstride = 1, 0
+        else:
+            d.model_out_nchw, d.model_out_cstride = 0, model_out.shape[3]
         d.noise, d.grad, d.coef = _p(noise), _p(grad), _p(coef)
         d.N, d.C, d.H, d.W, d.clip_denoised = N, Cc, H, W, int(clip_denoised)
         d.x_next, d.sample, d.mean, d.var, d.x0, d.eps = _p(x_next), _p(sample), _p(mean), _p(var), _p(x0), _p(eps)

@@ -42,6 +42,15 @@ def small_cfg():
     return c
 
 
+def mid_cfg():
+    """NFD-width (256 base channels, so every GroupNorm group is a multiple of 8 channels and every
+    GEMM K a multiple of 64 — the shapes the sm_100a kernels are written for) but 3 levels at 32x32:
+    small enough for the CPU oracle to run forward+backward in about a second."""
+    c = dict(NFD_CFG)
+    c.update(image_size=32, in_out_channels=32, channel_mult=(1, 2, 4), attention_resolutions="16,8", feat_layer=5)
+    return c
+
+
 def unet_structure(cfg):
     """Block list of UNetModel.__init__ (unet.py:480-616): returns (input, middle, output) where
     each block is a list of ('res', cin, cout, updown) / ('attn', ch, heads) entries."""

@@ -1,0 +1,18 @@
+"""Shared convolution test cases: (name, N, H, W, Cin, Cout, ksize, Cin2, bias, residual, accumulate, out_bf16, tune)."""
+CASES = [
+    ("k3_16x16_64_64", 1, 16, 16, 64, 64, 3, 0, True, False, False, False, None),
+    ("k3_32x32_128_256_res", 1, 32, 32, 128, 256, 3, 0, True, True, False, False, None),
+    ("k3_8x8_n2_128_128", 2, 8, 8, 128, 128, 3, 0, True, False, False, False, None),
+    ("k3_8x8_n1_256_256_splitk", 1, 8, 8, 256, 256, 3, 0, True, True, False, False, None),
+    ("k3_8x8_n3_64_64", 3, 8, 8, 64, 64, 3, 0, False, False, False, False, None),
+    ("k3_64x64_64_192", 1, 64, 64, 64, 192, 3, 0, True, False, False, False, None),
+    ("k1_32x32_256_768", 1, 32, 32, 256, 768, 1, 0, True, False, False, False, None),
+    ("k3_16x16_128_128_skip192", 1, 16, 16, 128, 128, 3, 192, True, False, False, False, None),
+    ("k3_128x128_64_64", 1, 128, 128, 64, 64, 3, 0, True, False, False, False, None),
+    ("k3_32x32_64_128_bf16out", 1, 32, 32, 64, 128, 3, 0, True, False, False, True, None),
+    ("k3_32x32_64_128_acc", 1, 32, 32, 64, 128, 3, 0, True, True, True, False, None),
+    ("k3_64x64_128_256_bn256", 1, 64, 64, 128, 256, 3, 0, True, False, False, False, {"block_n": 256, "stages": 4}),
+    ("k3_32x32_128_128_split3", 1, 32, 32, 128, 128, 3, 0, True, True, False, False, {"split_k": 3}),
+    ("k3_16x16_128_64_bn64_st2", 1, 16, 16, 128, 64, 3, 0, True, False, False, False, {"block_n": 64, "stages": 2}),
+    ("k1_16x16_n2_192_256", 2, 16, 16, 192, 256, 1, 0, False, True, False, False, None),
+]

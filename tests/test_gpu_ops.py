@@ -1,0 +1,228 @@
+"""GPU parity of every non-GEMM kernel against the pure-torch mirror (tests/ref_ops.py, CPU fp32).
+Call-site citations are in include/ishape_b200.h."""
+import math
+
+import pytest
+import torch
+
+from tests.conftest import rel_l2
+from tests.ref_ops import RefOps
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ishapediting_b200.ops import CudaOps
+
+    return CudaOps(torch.device(DEV), "bf16")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return RefOps("bf16")
+
+
+def G(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def test_layout_roundtrip(ops):
+    x = torch.randn(2, 12, 16, 24, generator=G(0))
+    for dt, tol in ((torch.float32, 0.0), (torch.bfloat16, 4e-3)):
+        y = ops.to_nhwc(x.to(DEV), ops.empty((2, 16, 24, 64), dt))
+        yc = y.float().cpu()
+        assert rel_l2(yc[..., :12], x.permute(0, 2, 3, 1)) <= tol
+        assert float(yc[..., 12:].abs().max()) == 0.0
+        back = ops.to_nchw(y, ops.empty((2, 12, 16, 24)))
+        assert rel_l2(back, x) <= tol
+
+
+GN_CASES = [
+    # N,H,W,C1,C2,film,silu,resample,raw
+    (1, 16, 16, 256, 0, False, True, 0, False),
+    (2, 8, 8, 512, 0, True, True, 0, False),
+    (1, 8, 8, 1024, 768, False, True, 0, True),      # concat: 56-channel groups straddle the two sources
+    (1, 16, 16, 256, 0, False, True, 1, False),      # down
+    (1, 8, 8, 256, 0, False, True, 2, False),        # up
+    (1, 32, 32, 512, 0, False, False, 0, False),     # attention norm (no silu)
+    (1, 64, 64, 256, 0, True, True, 0, False),       # multi-split statistics
+]
+
+
+@pytest.mark.parametrize("case", GN_CASES)
+def test_groupnorm_forward_backward(ops, ref, case):
+    N, H, W, C1, C2, film_on, silu, rs, want_raw = case
+    g = G(3)
+    C = C1 + C2
+    x1 = torch.randn(N, H, W, C1, generator=g) * 1.5 + 0.3
+    x2 = torch.randn(N, H, W, C2, generator=g) if C2 else None
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    film = 0.3 * torch.randn(N, 2 * C + 64, generator=g) if film_on else None
+    foff = 32 if film_on else 0
+    Ho, Wo = (H // 2, W // 2) if rs == 1 else ((H * 2, W * 2) if rs == 2 else (H, W))
+    d = lambda t: None if t is None else t.to(DEV)
+    for lo in (torch.float32, torch.bfloat16):
+        outs = {}
+        for name, o in (("ref", ref), ("cuda", ops)):
+            dev = "cpu" if name == "ref" else DEV
+            mv = (lambda t: None if t is None else t.to(dev))
+            stats = torch.zeros(N, 32, 2, device=dev)
+            y = torch.zeros(N, Ho, Wo, C, dtype=lo, device=dev)
+            raw = torch.zeros(N, H, W, C, dtype=lo, device=dev) if want_raw else None
+            xres = torch.zeros(N, Ho, Wo, C, device=dev) if rs else None
+            o.gn_forward(mv(x1), mv(x2), mv(gamma), mv(beta), mv(film), foff, silu, rs, stats, y, raw=raw, xres=xres)
+            outs[name] = (stats, y, raw, xres)
+        tol = 1e-5 if lo == torch.float32 else 6e-3
+        assert rel_l2(outs["cuda"][0], outs["ref"][0]) < 1e-5
+        assert rel_l2(outs["cuda"][1].float(), outs["ref"][1].float()) < tol
+        if want_raw:
+            assert rel_l2(outs["cuda"][2].float(), outs["ref"][2].float()) < tol
+        if rs:
+            assert rel_l2(outs["cuda"][3], outs["ref"][3]) < 1e-6
+    # backward
+    dy = torch.randn(N, Ho, Wo, C, generator=g)
+    for gres_mode in (None, "out", "in"):
+        gres = None if gres_mode is None else (torch.randn(N, Ho, Wo, C, generator=g) if gres_mode == "out"
+                                               else torch.randn(N, H, W, C, generator=g))
+        res = {}
+        for name, o in (("ref", ref), ("cuda", ops)):
+            dev = "cpu" if name == "ref" else DEV
+            mv = (lambda t: None if t is None else t.to(dev))
+            stats = torch.zeros(N, 32, 2, device=dev)
+            y = torch.zeros(N, Ho, Wo, C, device=dev)
+            o.gn_forward(mv(x1), mv(x2), mv(gamma), mv(beta), mv(film), foff, silu, rs, stats, y)
+            gx1 = torch.full((N, H, W, C1), 0.5, device=dev)      # accumulate into a non-zero buffer
+            gx1_lo = torch.zeros(N, H, W, C1, dtype=torch.bfloat16, device=dev)
+            gx2 = torch.zeros(N, H, W, C2, device=dev) if C2 else None
+            gx2_lo = torch.zeros(N, H, W, C2, dtype=torch.bfloat16, device=dev) if C2 else None
+            o.gn_backward(mv(x1), mv(x2), mv(gamma), mv(beta), mv(film), foff, silu, rs, stats, mv(dy), mv(gres),
+                          gres_mode == "in", gx1, True, gx1_lo, gx2, False, gx2_lo)
+            res[name] = (gx1, gx1_lo, gx2, gx2_lo)
+        assert rel_l2(res["cuda"][0], res["ref"][0]) < 2e-5, (case, gres_mode)
+        assert rel_l2(res["cuda"][1].float(), res["ref"][1].float()) < 6e-3
+        if C2:
+            assert rel_l2(res["cuda"][2], res["ref"][2]) < 2e-5
+            assert rel_l2(res["cuda"][3].float(), res["ref"][3].float()) < 6e-3
+
+
+@pytest.mark.parametrize("N,S,heads", [(1, 8, 2), (2, 16, 3), (1, 32, 4)])
+def test_attention_forward_backward(ops, ref, N, S, heads):
+    g = G(5)
+    C = heads * 64
+    T = S * S
+    qkv = torch.randn(N, S, S, 3 * C, generator=g)
+    d_out = torch.randn(N, S, S, C, generator=g)
+    r = {}
+    for name, o in (("ref", ref), ("cuda", ops)):
+        dev = "cpu" if name == "ref" else DEV
+        probs = torch.zeros(N, heads, T, T, device=dev)
+        out = torch.zeros(N, S, S, C, device=dev)
+        o.attention_forward(qkv.to(dev), heads, probs, out)
+        tmp = torch.zeros(N, heads, T, T, device=dev)
+        dq = torch.zeros(N, S, S, 3 * C, device=dev)
+        o.attention_backward(qkv.to(dev), probs, d_out.to(dev), heads, tmp, dq)
+        r[name] = (probs, out, dq)
+    assert rel_l2(r["cuda"][0], r["ref"][0]) < 1e-5
+    assert rel_l2(r["cuda"][1], r["ref"][1]) < 1e-5
+    assert rel_l2(r["cuda"][2], r["ref"][2]) < 2e-5
+
+
+def test_time_embed(ops, ref):
+    g = G(7)
+    mc, hid, rows, N = 64, 256, 1000, 3
+    t = torch.tensor([0, 246, 999])
+    from ishapediting_b200.guided_diffusion.nn import timestep_freqs
+
+    freqs = timestep_freqs(mc)
+    w1, b1 = torch.randn(hid, mc, generator=g) / 8, torch.randn(hid, generator=g) * 0.1
+    w2, b2 = torch.randn(hid, hid, generator=g) / 16, torch.randn(hid, generator=g) * 0.1
+    wa, ba = torch.randn(rows, hid, generator=g) / 16, torch.randn(rows, generator=g) * 0.1
+    out_ref = torch.zeros(N, rows)
+    ref.time_embed(t, freqs, w1, b1, w2, b2, wa, ba, None, out_ref)
+    c = lambda x: x.to(DEV)
+    out = ops.zeros((N, rows))
+    ops.time_embed(c(t), c(freqs), c(w1), c(b1), c(w2), c(b2), c(wa), c(ba), ops.empty((N * (mc + 2 * hid),)), out)
+    assert rel_l2(out, out_ref) < 2e-5
+
+
+@pytest.mark.parametrize("nchw", [False, True])
+def test_ddpm_step(ops, ref, nchw):
+    g = G(9)
+    N, C, H, W = 2, 12, 16, 16
+    x, noise, grad = (torch.randn(N, C, H, W, generator=g) for _ in range(3))
+    mo = torch.randn(N, 2 * C, H, W, generator=g) if nchw else torch.randn(N, H, W, 2 * C + 8, generator=g)
+    coef = torch.tensor([1.3, 0.8, 0.4, 0.6, -6.0, -3.0, 1.0, 600.0])
+    names = ("x_next", "sample", "mean", "var", "x0", "eps")
+    r = {}
+    for name, o in (("ref", ref), ("cuda", ops)):
+        dev = "cpu" if name == "ref" else DEV
+        outs = {k: torch.zeros(N, C, H, W, device=dev) for k in names}
+        o.ddpm_step(x.to(dev), mo.to(dev), coef.to(dev), True, noise=noise.to(dev), grad=grad.to(dev), **outs)
+        r[name] = outs
+    for k in names:
+        assert rel_l2(r["cuda"][k], r["ref"][k]) < 1e-5, k
+
+
+def test_drag_loss_grad(ops, ref):
+    from ishapediting_b200.drag_utils import DragGeometry, align_maps
+
+    S, Cf = 16, 128
+    g = G(11)
+    chan_map, inv_map, Ca = align_maps(Cf)
+    feat = torch.randn(1, S, S, Cf, generator=g)
+    origin = torch.randn(3, S, S, Ca, generator=g)
+    sources = (torch.rand(3, 3, generator=g) - 0.5).numpy()
+    targets = sources + (torch.rand(3, 3, generator=g).numpy() - 0.5) * 0.4
+    targets[2] = [0.97, -0.99, 0.5]     # patch partly outside the plane -> zero padding path
+    geo = DragGeometry(sources, targets, r=3, voxel_size=2.0 / 64, S=S, Ca=Ca)
+    for loss_type in (0, 1):
+        for cof in (0.2, 0.0):
+            r = {}
+            for name, o in (("ref", ref), ("cuda", ops)):
+                dev = "cpu" if name == "ref" else DEV
+                t = geo.to(dev)
+                npts = t.patch_xy.shape[1]
+                gbuf = torch.zeros(3, npts, Ca, device=dev)
+                info = torch.zeros(3, npts, 4, device=dev)
+                partial = torch.zeros(o.drag_partial_len(S, Cf, npts), dtype=torch.float64, device=dev)
+                loss = torch.zeros(1, device=dev)
+                d_feat = torch.full((1, S, S, Cf), 7.0, device=dev)
+                o.drag_loss_grad(feat.to(dev), origin.to(dev), chan_map.to(dev), inv_map.to(dev), t.patch_xy,
+                                 t.shift_xy, t.weight, t.group_size, t.bbox, t.mask, t.mask_count, t.inv_count, cof,
+                                 loss_type, gbuf, info, partial, loss, d_feat)
+                r[name] = (loss, d_feat)
+            assert rel_l2(r["cuda"][0], r["ref"][0]) < 1e-5, (loss_type, cof)
+            assert rel_l2(r["cuda"][1], r["ref"][1]) < 2e-5, (loss_type, cof)
+
+
+def test_resize_feat_align(ops, ref):
+    from ishapediting_b200.drag_utils import align_maps
+
+    S, Cf = 8, 128
+    chan_map, _, Ca = align_maps(Cf)
+    feat = torch.randn(1, S, S, Cf, generator=G(13))
+    a = ref.resize_feat_align(feat, chan_map, torch.zeros(3, S, S, Ca))
+    b = ops.resize_feat_align(feat.to(DEV), chan_map.to(DEV), ops.empty((3, S, S, Ca)))
+    assert torch.equal(a, b.cpu())
+
+
+def test_triplane_decode(ops, ref):
+    g = G(15)
+    R = 32
+    planes = torch.randn(3, R, R, 32, generator=g) * 0.3
+    weights = [torch.randn(32, 64, generator=g)] + [
+        t for o_, i_ in ((128, 128), (128, 128), (1, 128))
+        for t in ((torch.rand(o_, i_, generator=g) * 2 - 1) / math.sqrt(i_), (torch.rand(o_, generator=g) * 2 - 1) / math.sqrt(i_))]
+    coords = torch.rand(1000, 3, generator=g) * 2.2 - 1.1     # some outside [-1,1]: zero padding
+    out_ref = ref.decode_points(planes, weights, coords, torch.zeros(1000))
+    wd = [w.to(DEV).contiguous() for w in weights]
+    out = ops.decode_points(planes.to(DEV), wd, coords.to(DEV), ops.empty((1000,)))
+    assert float((out.cpu() - out_ref).abs().max()) < 2e-4 * max(1.0, float(out_ref.abs().max()))
+    res = 20
+    lin = torch.linspace(-1, 1, res)
+    g_ref = ref.decode_grid(planes, weights, lin, 3, 11, torch.zeros(8 * res * res))
+    g_out = ops.decode_grid(planes.to(DEV), wd, lin.to(DEV), 3, 11, ops.empty((8 * res * res,)))
+    assert float((g_out.cpu() - g_ref).abs().max()) < 2e-4 * max(1.0, float(g_ref.abs().max()))
+    assert float(((g_out.cpu() > 0) != (g_ref > 0)).float().mean()) < 1e-3
