@@ -23,7 +23,7 @@ constexpr int TC_UMMA_K = 16;
 constexpr int TC_A_STAGE = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KiB
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM_LIMIT = 227 * 1024;
+constexpr int TC_SMEM_LIMIT = 227 * 1024 - 2048;  // dynamic part; the kernel also has ~150 B of static smem (barriers)
 
 struct TcParams {
   int tw, th, nb;

@@ -44,10 +44,10 @@ if __name__ == "__main__":
     for case in CASES:
         if which != "all" and case[0] != which:
             continue
-        if mode == "fp32" and case[9]:
+        if mode == "fp32" and case[11]:
             continue
         err, mx, o, r = run_case(ops, case, mode)
-        tol = 1e-2 if case[9] else (2e-3 if mode == "bf16" else 1e-5)
+        tol = 1e-2 if case[11] else (2e-3 if mode == "bf16" else 1e-5)
         print(f"[probe_conv {mode}] {case[0]:34s} rel_l2={err:.3e} max_abs={mx:.3e} {'OK' if err < tol else 'FAIL'}", flush=True)
         if err >= tol:
             bad = (o - r).abs()
