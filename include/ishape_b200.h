@@ -89,6 +89,8 @@ typedef struct isb_conv_desc {
   int split_k;
   int stages;
 } isb_conv_desc;
+/* Workspace (split-K partial tiles + arrival counters): must be ZERO-FILLED by the caller before its
+ * first use; every launch leaves the counters at zero again, so one buffer serves all layers. */
 size_t isb_conv2d_workspace(const isb_conv_desc* d);
 int isb_conv2d(const isb_conv_desc* d, void* workspace, size_t workspace_bytes,
                isb_stream_t stream);

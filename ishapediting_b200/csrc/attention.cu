@@ -87,6 +87,122 @@ bgemm_kernel(const BgemmParams p) {
   }
 }
 
+// ---- bf16 tensor-core variant (mma.sync m16n8k16, fp32 accumulate) -------------------------
+// Same contract as bgemm_kernel; operands are read as fp32 and rounded to bf16 on their way into
+// shared memory ("bf16 mode": q, k, v, P and dS are bf16 MMA operands, softmax stays fp32).
+constexpr int TG_BM = 64, TG_BN = 64, TG_BK = 32, TG_LD = TG_BK + 8;  // 80-byte rows: conflict-free fragment loads
+
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// stage a [64 rows x 32 k] operand tile into smem as bf16, rows = m (or n), k contiguous
+template <bool KMAJOR>
+__device__ __forceinline__ void tg_load_tile(const float* __restrict__ src, int ld, int row0, int k0,
+                                             __nv_bfloat16 (*sm)[TG_LD]) {
+  const int tid = threadIdx.x;
+  if (KMAJOR) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 128;
+      const int r = idx >> 3, kv = (idx & 7) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(row0 + r) * ld + k0 + kv));
+      uint2 u;
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(&sm[r][kv]) = u;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 128;
+      const int k = idx >> 4, rv = (idx & 15) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(k0 + k) * ld + row0 + rv));
+      sm[rv + 0][k] = __float2bfloat16_rn(v.x);
+      sm[rv + 1][k] = __float2bfloat16_rn(v.y);
+      sm[rv + 2][k] = __float2bfloat16_rn(v.z);
+      sm[rv + 3][k] = __float2bfloat16_rn(v.w);
+    }
+  }
+}
+
+template <bool A_K, bool B_K>
+__global__ void __launch_bounds__(128)
+bgemm_mma_kernel(const BgemmParams p) {
+  __shared__ __align__(16) __nv_bfloat16 As[TG_BM][TG_LD];
+  __shared__ __align__(16) __nv_bfloat16 Bs[TG_BN][TG_LD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int g = lane >> 2, t = lane & 3;
+  const int bz = blockIdx.z;
+  const int bo = bz / p.inner, bi = bz % p.inner;
+  const float* A = p.A + bo * p.a_b0 + bi * p.a_b1;
+  const float* B = p.B + bo * p.b_b0 + bi * p.b_b1;
+  const int m0 = blockIdx.x * TG_BM, n0 = blockIdx.y * TG_BN;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+
+  for (int k0 = 0; k0 < p.K; k0 += TG_BK) {
+    __syncthreads();
+    tg_load_tile<A_K>(A, p.lda, m0, k0, As);
+    tg_load_tile<B_K>(B, p.ldb, n0, k0, Bs);
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TG_BK; kk += 16) {
+      uint32_t af[2][4], bf[4][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int r = wm * 32 + mi * 16 + g;
+        af[mi][0] = *reinterpret_cast<const uint32_t*>(&As[r][kk + 2 * t]);
+        af[mi][1] = *reinterpret_cast<const uint32_t*>(&As[r + 8][kk + 2 * t]);
+        af[mi][2] = *reinterpret_cast<const uint32_t*>(&As[r][kk + 2 * t + 8]);
+        af[mi][3] = *reinterpret_cast<const uint32_t*>(&As[r + 8][kk + 2 * t + 8]);
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int c = wn * 32 + ni * 8 + g;
+        bf[ni][0] = *reinterpret_cast<const uint32_t*>(&Bs[c][kk + 2 * t]);
+        bf[ni][1] = *reinterpret_cast<const uint32_t*>(&Bs[c][kk + 2 * t + 8]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) mma_bf16_16816(acc[mi][ni], af[mi], bf[ni]);
+    }
+  }
+  const long long coff = bo * p.c_b0 + bi * p.c_b1;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = m0 + wm * 32 + mi * 16 + g + h * 8;
+        const int col = n0 + wn * 32 + ni * 8 + 2 * t;
+        const size_t off = static_cast<size_t>(coff) + static_cast<size_t>(row) * p.ldc + col;
+        const float v0 = acc[mi][ni][2 * h] * p.alpha, v1 = acc[mi][ni][2 * h + 1] * p.alpha;
+        if (p.c_dtype == ISB_BF16) *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = pack_bf16x2(v0, v1);
+        else *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.C) + off) = make_float2(v0, v1);
+      }
+}
+
+template <bool A_K, bool B_K>
+static int bgemm_mma(const BgemmParams& p, int batches, cudaStream_t st) {
+  ISB_CHECK_ARG(p.M % TG_BM == 0 && p.N % TG_BN == 0 && p.K % TG_BK == 0, "attention gemm (mma): M=%d N=%d K=%d must be multiples of 64/64/32", p.M, p.N, p.K);
+  dim3 grid(p.M / TG_BM, p.N / TG_BN, batches);
+  bgemm_mma_kernel<A_K, B_K><<<grid, 128, 0, st>>>(p);
+  ISB_LAUNCH_CHECK();
+  return ISB_OK;
+}
+
 template <bool A_K, bool B_K>
 static int bgemm(const BgemmParams& p, int batches, cudaStream_t st) {
   ISB_CHECK_ARG(p.M % BG_BM == 0 && p.N % BG_BN == 0 && p.K % BG_BK == 0, "attention gemm: M=%d N=%d K=%d must be multiples of 64/64/16", p.M, p.N, p.K);
@@ -94,6 +210,11 @@ static int bgemm(const BgemmParams& p, int batches, cudaStream_t st) {
   bgemm_kernel<A_K, B_K><<<grid, 256, 0, st>>>(p);
   ISB_LAUNCH_CHECK();
   return ISB_OK;
+}
+
+template <bool A_K, bool B_K>
+static int bgemm_any(const BgemmParams& p, int batches, bool tensor_cores, cudaStream_t st) {
+  return tensor_cores ? bgemm_mma<A_K, B_K>(p, batches, st) : bgemm<A_K, B_K>(p, batches, st);
 }
 
 // one block (128 threads) per row of length T: in-place fp32 softmax (unet.py:352)
@@ -182,7 +303,8 @@ int isb_attention_forward(const float* qkv, int N, int T, int heads, int ch, flo
   p.b_b0 = p.a_b0; p.b_b1 = p.a_b1;
   p.c_b0 = heads * TT; p.c_b1 = TT;
   p.inner = heads; p.alpha = 1.0f / sqrtf(static_cast<float>(ch)); p.c_dtype = ISB_F32;
-  int rc = isb::bgemm<true, true>(p, N * heads, st);
+  const bool tc = out_dtype == ISB_BF16;   // bf16 mode -> tensor cores; fp32 mode -> FFMA
+  int rc = isb::bgemm_any<true, true>(p, N * heads, tc, st);
   if (rc) return rc;
   isb::softmax_rows_kernel<<<N * heads * T, 128, 0, st>>>(probs, T);
   ISB_LAUNCH_CHECK();
@@ -194,7 +316,7 @@ int isb_attention_forward(const float* qkv, int N, int T, int heads, int ch, flo
   p.b_b0 = static_cast<long long>(T) * 3 * C; p.b_b1 = 3 * ch;
   p.c_b0 = static_cast<long long>(T) * C; p.c_b1 = ch;
   p.alpha = 1.0f; p.c_dtype = out_dtype;
-  return isb::bgemm<true, false>(p, N * heads, st);
+  return isb::bgemm_any<true, false>(p, N * heads, tc, st);
 }
 
 int isb_attention_backward(const float* qkv, const float* probs, const float* d_out, int N, int T, int heads,
@@ -218,7 +340,8 @@ int isb_attention_backward(const float* qkv, const float* probs, const float* d_
   p.b_b0 = static_cast<long long>(T) * C; p.b_b1 = ch;
   p.c_b0 = qkv_b0; p.c_b1 = 3 * ch;
   p.alpha = 1.0f; p.c_dtype = lo_dtype;
-  int rc = isb::bgemm<false, false>(p, N * heads, st);
+  const bool tc = lo_dtype == ISB_BF16;
+  int rc = isb::bgemm_any<false, false>(p, N * heads, tc, st);
   if (rc) return rc;
   // dP[t,s] = sum_c dO[t,c] V[s,c]
   p.A = d_out; p.B = qkv + 2 * ch; p.C = tmp;
@@ -228,7 +351,7 @@ int isb_attention_backward(const float* qkv, const float* probs, const float* d_
   p.b_b0 = qkv_b0; p.b_b1 = 3 * ch;
   p.c_b0 = heads * TT; p.c_b1 = TT;
   p.alpha = 1.0f; p.c_dtype = ISB_F32;
-  rc = isb::bgemm<true, true>(p, N * heads, st);
+  rc = isb::bgemm_any<true, true>(p, N * heads, tc, st);
   if (rc) return rc;
   isb::softmax_bwd_rows_kernel<<<N * heads * T, 128, 0, st>>>(probs, tmp, T, alpha);
   ISB_LAUNCH_CHECK();
@@ -240,12 +363,12 @@ int isb_attention_backward(const float* qkv, const float* probs, const float* d_
   p.b_b0 = qkv_b0; p.b_b1 = 3 * ch;
   p.c_b0 = qkv_b0; p.c_b1 = 3 * ch;
   p.alpha = 1.0f; p.c_dtype = lo_dtype;
-  rc = isb::bgemm<true, false>(p, N * heads, st);
+  rc = isb::bgemm_any<true, false>(p, N * heads, tc, st);
   if (rc) return rc;
   // dK[s,c] = sum_t dS[t,s] Q[t,c]
   p.A = tmp; p.B = qkv; p.C = dq + static_cast<size_t>(ch) * esz;
   p.lda = T; p.ldb = 3 * C; p.ldc = 3 * C;
-  return isb::bgemm<false, false>(p, N * heads, st);
+  return isb::bgemm_any<false, false>(p, N * heads, tc, st);
 }
 
 }  // extern "C"

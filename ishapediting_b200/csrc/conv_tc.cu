@@ -12,7 +12,8 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
 // warps 2..5 = epilogue (TMEM lanes 32*(warp%4) ..).  Split-K partials go to a
-// caller workspace and are reduced in fixed order (deterministic).
+// caller workspace; the last CTA to arrive for an output tile reduces them in fixed order
+// (deterministic) and runs the epilogue — no separate reduction launch.
 #include "common.cuh"
 
 namespace isb {
@@ -38,7 +39,8 @@ struct TcParams {
   void* out;
   int out_dtype;
   int accumulate;
-  float* partial;  // != nullptr when splits > 1
+  float* partial;  // != nullptr when splits > 1: [tile][split][128][block_n] fp32
+  int* counters;   // [tiles] arrival counters (zero between launches)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------
@@ -151,6 +153,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ int split_is_last;
 
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
@@ -264,66 +267,107 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int n = n0 + pn;
     const bool valid = n < p.N;
     const size_t m = (static_cast<size_t>(n) * p.H + (h0 + ph_)) * p.W + (w0 + pw_);
-    const size_t m_total = static_cast<size_t>(p.N) * p.H * p.W;
+    const int nchunks = p.block_n / 32;
 
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tc_fence_after();
-    const int nchunks = p.block_n / 32;
-    for (int c = 0; c < nchunks; ++c) {
-      const int col0 = cout0 + c * 32;
-      if (col0 >= p.Cout) break;  // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
-      tmem_ld_wait();
-      if (!valid) continue;
-      float f[32];
+
+    bool do_final = true;
+    const size_t tile_id = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
+    if (p.splits > 1) {
+      // Split-K: every CTA parks its fp32 partial tile in the workspace; the LAST CTA to arrive for this
+      // output tile folds all partials in split order (deterministic) and runs the real epilogue.
+      float* mine = p.partial + ((tile_id * p.splits + split) * TC_BLOCK_M + r) * p.block_n;
+      for (int c = 0; c < nchunks; ++c) {
+        if (cout0 + c * 32 >= p.Cout) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(mine + c * 32);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (p.partial != nullptr) {
-        float4* dst = reinterpret_cast<float4*>(p.partial + (static_cast<size_t>(split) * m_total + m) * p.Cout + col0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        continue;
-      }
-      const size_t off = m * p.Cout + col0;
-      if (p.bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(b4 + j);
-          f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+          for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       }
-      if (p.residual != nullptr) {
-        const float4* r4 = reinterpret_cast<const float4*>(p.residual + off);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(r4 + j);
-          f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-        }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const int prev = atomicAdd(p.counters + tile_id, 1);
+        const int last = (prev == p.splits - 1);
+        if (last) p.counters[tile_id] = 0;  // leave the workspace ready for the next launch
+        split_is_last = last;
       }
-      if (p.out_dtype == ISB_BF16) {
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      do_final = split_is_last != 0;
+      if (do_final) __threadfence();
+    }
+
+    if (do_final) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int col0 = cout0 + c * 32;
+        if (col0 >= p.Cout) break;  // warp-uniform
+        float f[32];
+        if (p.splits > 1) {
+          if (!valid) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
-          u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-          u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-          u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-          dst[j] = u;
+          for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          for (int s2 = 0; s2 < p.splits; ++s2) {
+            const float4* src = reinterpret_cast<const float4*>(
+                p.partial + ((tile_id * p.splits + s2) * TC_BLOCK_M + r) * p.block_n + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t4 = __ldcg(src + j);
+              f[4 * j] += t4.x; f[4 * j + 1] += t4.y; f[4 * j + 2] += t4.z; f[4 * j + 3] += t4.w;
+            }
+          }
+        } else {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_wait();
+          if (!valid) continue;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         }
-      } else {
-        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
-        if (p.accumulate) {
+        const size_t off = m * p.Cout + col0;
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 o = dst[j];
-            f[4 * j] += o.x; f[4 * j + 1] += o.y; f[4 * j + 2] += o.z; f[4 * j + 3] += o.w;
+            const float4 b = __ldg(b4 + j);
+            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
           }
         }
+        if (p.residual != nullptr) {
+          const float4* r4 = reinterpret_cast<const float4*>(p.residual + off);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(r4 + j);
+            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+          }
+        }
+        if (p.out_dtype == ISB_BF16) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+            u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+            u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            dst[j] = u;
+          }
+        } else {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+          if (p.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 o = dst[j];
+              f[4 * j] += o.x; f[4 * j + 1] += o.y; f[4 * j + 2] += o.z; f[4 * j + 3] += o.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
       }
     }
   }
@@ -337,50 +381,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
-// out = (acc ? out : 0) + bias + residual + sum_s partial[s]   (fixed order: deterministic)
-__global__ void __launch_bounds__(256)
-splitk_finalize_kernel(const float* __restrict__ partial, int splits, size_t m_total, int Cout,
-                       const float* __restrict__ bias, const float* __restrict__ residual, void* out,
-                       int out_dtype, int accumulate) {
-  const size_t total8 = m_total * Cout / 8;
-  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total8) return;
-  const size_t e = idx * 8;
-  const int col = static_cast<int>(e % Cout);
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const size_t plane = m_total * Cout;
-  for (int s = 0; s < splits; ++s) {
-    float v[8];
-    load8(partial + s * plane + e, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += v[j];
-  }
-  if (bias) {
-    float v[8];
-    load8(bias + col, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += v[j];
-  }
-  if (residual) {
-    float v[8];
-    load8(residual + e, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += v[j];
-  }
-  if (accumulate && out_dtype == ISB_F32) {
-    const float4* o = reinterpret_cast<const float4*>(reinterpret_cast<float*>(out) + e);
-    const float4 a = o[0], b = o[1];
-    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-  }
-  store8(out, e, out_dtype, acc);
-}
-
 // ---- host side --------------------------------------------------------------
 struct TcPlan {
   TcParams p;
   int smem_bytes;
   size_t ws_bytes;
+  size_t counter_bytes;
   dim3 grid;
 };
 
@@ -418,41 +424,59 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   p.chunks1 = d->a2 ? d->Cin2 / 64 : 0;
   p.k_iters = p.ntaps * p.chunks0 + p.chunks1;
   const int mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  // N tile
+  // N tile / split-K / pipeline depth.  Goal: about one CTA per SM (or two when two fit), each with
+  // at least two k-iterations; small-M layers are weight-streaming bound, so they trade a narrower
+  // N tile for more CTAs pulling weights concurrently.
+  const int sms = num_sms();
+  auto splits_for = [&](int tiles) {
+    int sp = 1;
+    if (tiles < sms) {
+      sp = sms / tiles;
+      if (sp > p.k_iters / 2) sp = p.k_iters / 2;
+      if (sp > 32) sp = 32;
+      if (sp < 1) sp = 1;
+    }
+    return sp;
+  };
   int bn = d->block_n;
   if (bn == 0) {
     if (d->Cout < 128) bn = d->Cout;                                  // 32,64,96
     else if (d->Cout % 128 != 0 && d->Cout <= 256) bn = d->Cout;      // e.g. 192: one exact tile
-    else bn = 128;
-    if (d->Cout % 256 == 0 && static_cast<long long>(mtiles) * (d->Cout / 128) >= 4LL * num_sms()) bn = 256;
+    else {
+      bn = 128;
+      const int t128 = mtiles * cdiv(d->Cout, 128), t64 = mtiles * cdiv(d->Cout, 64);
+      if (d->Cout % 64 == 0 && t128 < sms &&
+          static_cast<long long>(t64) * splits_for(t64) * 10 > static_cast<long long>(t128) * splits_for(t128) * 13)
+        bn = 64;
+    }
   }
   ISB_CHECK_ARG(bn >= 32 && bn <= 256 && bn % 32 == 0, "conv_tc: block_n=%d must be a multiple of 32 in [32,256]", bn);
   p.block_n = bn;
   p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
   const int ntiles = cdiv(d->Cout, bn);
   const int tiles = mtiles * ntiles;
-  int splits = d->split_k;
-  if (splits == 0) {
-    splits = 1;
-    if (tiles < (num_sms() * 3) / 4) {
-      splits = cdiv(num_sms(), tiles);
-      if (splits > p.k_iters / 2) splits = p.k_iters / 2;
-      if (splits > 32) splits = 32;
-      if (splits < 1) splits = 1;
-    }
-  }
+  int splits = d->split_k ? d->split_k : splits_for(tiles);
   ISB_CHECK_ARG(splits >= 1 && splits <= p.k_iters, "conv_tc: split_k=%d out of range (k_iters=%d)", splits, p.k_iters);
   p.splits = splits;
   const int stage_bytes = TC_A_STAGE + bn * 128;
-  int stages = d->stages;
-  if (stages == 0) stages = bn <= 128 ? 3 : 4;
   const int max_stages = (TC_SMEM_LIMIT - 1024) / stage_bytes;
+  int stages = d->stages;
+  if (stages == 0) {
+    if (static_cast<long long>(tiles) * splits <= sms) {
+      stages = 6;                                   // alone on its SM: prefetch as deep as smem allows
+      const int per_cta = cdiv(p.k_iters, splits);
+      if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
+    } else {
+      stages = bn <= 128 ? 3 : 4;                   // leave room for a second resident CTA
+    }
+  }
   if (stages > max_stages) stages = max_stages;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   ISB_CHECK_ARG(stages >= 2, "conv_tc: not enough shared memory for 2 stages");
   p.stages = stages;
   plan->smem_bytes = stages * stage_bytes + 1024;
-  plan->ws_bytes = splits > 1 ? static_cast<size_t>(splits) * d->N * d->H * d->W * d->Cout * sizeof(float) : 0;
+  plan->counter_bytes = (static_cast<size_t>(mtiles) * ntiles * sizeof(int) + 255) & ~static_cast<size_t>(255);
+  plan->ws_bytes = splits > 1 ? plan->counter_bytes + static_cast<size_t>(mtiles) * ntiles * splits * TC_BLOCK_M * bn * sizeof(float) : 0;
   plan->grid = dim3(mtiles, ntiles, splits);
   p.bias = d->bias;
   p.residual = d->residual;
@@ -460,6 +484,7 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   p.out_dtype = d->out_dtype;
   p.accumulate = d->accumulate;
   p.partial = nullptr;
+  p.counters = nullptr;
   return ISB_OK;
 }
 
@@ -523,7 +548,8 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
       set_error("conv_tc: workspace %zu bytes < required %zu", ws_bytes, plan.ws_bytes);
       return ISB_ERR_WORKSPACE;
     }
-    p.partial = static_cast<float*>(ws);
+    p.counters = static_cast<int*>(ws);
+    p.partial = reinterpret_cast<float*>(static_cast<char*>(ws) + plan.counter_bytes);
   }
   CUtensorMap mapA, mapA2, mapB;
   rc = encode_act_map(&mapA, d->a, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.nb);
@@ -539,14 +565,6 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
   if (rc) return rc;
   conv_tc_kernel<<<plan.grid, TC_THREADS, plan.smem_bytes, stream>>>(mapA, mapA2, mapB, p);
   ISB_LAUNCH_CHECK();
-  if (p.splits > 1) {
-    const size_t m_total = static_cast<size_t>(d->N) * d->H * d->W;
-    const size_t total8 = m_total * d->Cout / 8;
-    splitk_finalize_kernel<<<cdiv(total8, 256), 256, 0, stream>>>(p.partial, p.splits, m_total, d->Cout, d->bias,
-                                                                  d->residual, d->out, d->out_dtype,
-                                                                  d->accumulate);
-    ISB_LAUNCH_CHECK();
-  }
   return ISB_OK;
 }
 

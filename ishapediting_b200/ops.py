@@ -60,7 +60,8 @@ class CudaOps:
         if self._ws is None or self._ws.numel() < nbytes:
             if torch.cuda.is_current_stream_capturing():
                 raise _lib.IsbError("conv workspace must be sized by an eager warm-up before graph capture")
-            self._ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+            # zero-filled: the split-K arrival counters at its head must start (and are left) at 0
+            self._ws = torch.zeros(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
         return self._ws, self._ws.numel()
 
     def _scratch(self, N, groups=32):

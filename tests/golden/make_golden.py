@@ -129,4 +129,4 @@ if __name__ == "__main__":
     if which in ("all", "decoder"):
         make_decoder()
     if which in ("all", "nfd"):
-        make_case(O.NFD_CFG, "nfd_step.npz", w_time=1, r1=12, voxel=2.0 / 256, full=False)
+        make_case(O.NFD_CFG, "nfd_step.npz", w_time=2, r1=12, voxel=2.0 / 256, full=False)
