@@ -144,8 +144,31 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// bias + residual (+ previous out) and store 8 consecutive output channels
+__device__ __forceinline__ void epilogue_store8(const TcParams& p, float* f, size_t off, int col) {
+  if (p.bias != nullptr) {
+    float b[8];
+    load8(p.bias + col, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += b[j];
+  }
+  if (p.residual != nullptr) {
+    float b[8];
+    load8(p.residual + off, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += b[j];
+  }
+  if (p.out_dtype == ISB_F32 && p.accumulate) {
+    const float4* o = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + off);
+    const float4 a = o[0], b = o[1];
+    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
+    f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+  }
+  store8(p.out, off, p.out_dtype, f);
+}
+
 // ---- the kernel -------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -302,72 +325,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (do_final) __threadfence();
     }
 
-    if (do_final) {
+    if (do_final && p.splits == 1) {
       for (int c = 0; c < nchunks; ++c) {
         const int col0 = cout0 + c * 32;
         if (col0 >= p.Cout) break;  // warp-uniform
-        float f[32];
-        if (p.splits > 1) {
-          if (!valid) continue;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = 0.f;
-          for (int s2 = 0; s2 < p.splits; ++s2) {
-            const float4* src = reinterpret_cast<const float4*>(
-                p.partial + ((tile_id * p.splits + s2) * TC_BLOCK_M + r) * p.block_n + c * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t4 = __ldcg(src + j);
-              f[4 * j] += t4.x; f[4 * j + 1] += t4.y; f[4 * j + 2] += t4.z; f[4 * j + 3] += t4.w;
-            }
-          }
-        } else {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
-          tmem_ld_wait();
-          if (!valid) continue;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        }
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+        if (!valid) continue;
         const size_t off = m * p.Cout + col0;
-        if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-          }
+        for (int j8 = 0; j8 < 4; ++j8) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
+          epilogue_store8(p, f, off + j8 * 8, col0 + j8 * 8);
         }
-        if (p.residual != nullptr) {
-          const float4* r4 = reinterpret_cast<const float4*>(p.residual + off);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(r4 + j);
-            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-          }
+      }
+    } else if (do_final) {
+      // fold: the 128 epilogue threads sweep the tile as a flat array (coalesced 32 B per thread),
+      // summing the partials in split order
+      const int et = threadIdx.x - 64;
+      const int vec_per_row = p.block_n / 8;
+      const int nvec = TC_BLOCK_M * vec_per_row;
+      const size_t tile_elems = static_cast<size_t>(TC_BLOCK_M) * p.block_n;
+      const float* tile_base = p.partial + tile_id * p.splits * tile_elems;
+      for (int idx = et; idx < nvec; idx += 128) {
+        const int rr = idx / vec_per_row;
+        const int cc = (idx - rr * vec_per_row) * 8;
+        const int col = cout0 + cc;
+        const int rn = rr / per_img;
+        const int rrem = rr - rn * per_img;
+        const int rh = rrem / p.tw;
+        const int rw = rrem - rh * p.tw;
+        if (n0 + rn >= p.N || col >= p.Cout) continue;
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const float* src = tile_base + static_cast<size_t>(rr) * p.block_n + cc;
+        for (int s2 = 0; s2 < p.splits; ++s2) {
+          const float4 u0 = __ldcg(reinterpret_cast<const float4*>(src));
+          const float4 u1 = __ldcg(reinterpret_cast<const float4*>(src) + 1);
+          f[0] += u0.x; f[1] += u0.y; f[2] += u0.z; f[3] += u0.w;
+          f[4] += u1.x; f[5] += u1.y; f[6] += u1.z; f[7] += u1.w;
+          src += tile_elems;
         }
-        if (p.out_dtype == ISB_BF16) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            u.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
-            u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-            u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            dst[j] = u;
-          }
-        } else {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
-          if (p.accumulate) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 o = dst[j];
-              f[4 * j] += o.x; f[4 * j + 1] += o.y; f[4 * j + 2] += o.z; f[4 * j + 3] += o.w;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        }
+        const size_t mm = (static_cast<size_t>(n0 + rn) * p.H + (h0 + rh)) * p.W + (w0 + rw);
+        epilogue_store8(p, f, mm * p.Cout + col, col);
       }
     }
   }

@@ -1,0 +1,214 @@
+"""Host-side logic on CPU: the UNet plan (forward + manual input-gradient backward), the guided step,
+the diffusion API mirrors, resize_feat_align index maps and the drag geometry — executed with the
+pure-torch operator mirror (tests/ref_ops.py) in place of the CUDA library and compared with the
+oracle.  This validates everything except the kernels themselves (those are the `-m gpu` tests)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nfd_oracle as O
+from tests.conftest import rel_l2
+from tests.helpers import build_model, drag_problem, seeded_inputs
+from tests.ref_ops import RefOps
+
+
+@pytest.fixture(scope="module")
+def small():
+    cfg = O.small_cfg()
+    sd = O.synth_state_dict(cfg)
+    model, diff = build_model(cfg, sd, "fp32", "cpu", RefOps("fp32"))
+    return cfg, sd, model, diff
+
+
+def test_state_dict_names_match_reference_layout(small):
+    cfg, sd, model, _ = small
+    assert list(model.state_dict().keys()) == [n for n, _ in O.unet_param_shapes(cfg)]
+
+
+def test_plan_forward_backward_matches_oracle(small):
+    cfg, sd, model, _ = small
+    g, x, _, _ = seeded_inputs(cfg)
+    t = torch.tensor([246])
+    xr = x.clone().requires_grad_(True)
+    o_ref, f_ref = O.unet_forward(sd, cfg, xr, t, 8)
+    proj, projo = torch.randn(f_ref.shape, generator=g), torch.randn(o_ref.shape, generator=g)
+    ((f_ref * proj).sum() + (o_ref * projo).sum()).backward()
+    xd = x.clone().requires_grad_(True)
+    o, f = model(xd, t, feat_layer=8)
+    ((f * proj).sum() + (o * projo).sum()).backward()
+    assert rel_l2(o.detach(), o_ref.detach()) < 1e-5
+    assert rel_l2(f.detach(), f_ref.detach()) < 1e-5
+    assert rel_l2(xd.grad, xr.grad) < 1e-5
+
+
+def test_plan_feature_only_gradient_and_batch(small):
+    cfg, sd, model, _ = small
+    g, x, x2, _ = seeded_inputs(cfg)
+    xb = torch.cat([x, x2])
+    t = torch.tensor([5, 999])
+    with torch.no_grad():
+        assert rel_l2(model(xb, t), O.unet_forward(sd, cfg, xb, t)) < 1e-5
+    for fl in (5, 8, 10):
+        xr = x.clone().requires_grad_(True)
+        _, f_ref = O.unet_forward(sd, cfg, xr, t[:1], fl)
+        proj = torch.randn(f_ref.shape, generator=g)
+        (f_ref * proj).sum().backward()
+        xd = x.clone().requires_grad_(True)
+        _, f = model(xd, t[:1], feat_layer=fl)
+        (f * proj).sum().backward()
+        assert rel_l2(xd.grad, xr.grad) < 1e-5, fl
+
+
+def test_backward_after_second_forward_is_refused(small):
+    cfg, _, model, _ = small
+    _, x, x2, _ = seeded_inputs(cfg)
+    xd = x.clone().requires_grad_(True)
+    _, f = model(xd, torch.tensor([3]), feat_layer=8)
+    with torch.no_grad():
+        model(x2, torch.tensor([3]))
+    with pytest.raises(RuntimeError):
+        f.sum().backward()
+
+
+def test_bf16_mode_emulation_within_tolerance():
+    cfg = O.small_cfg()
+    sd = O.synth_state_dict(cfg)
+    model, _ = build_model(cfg, sd, "bf16", "cpu", RefOps("bf16"))
+    g, x, _, _ = seeded_inputs(cfg)
+    t = torch.tensor([246])
+    xr = x.clone().requires_grad_(True)
+    o_ref, f_ref = O.unet_forward(sd, cfg, xr, t, 8)
+    proj = torch.randn(f_ref.shape, generator=g)
+    (f_ref * proj).sum().backward()
+    xd = x.clone().requires_grad_(True)
+    o, f = model(xd, t, feat_layer=8)
+    (f * proj).sum().backward()
+    assert max(rel_l2(o.detach(), o_ref.detach()), rel_l2(f.detach(), f_ref.detach()), rel_l2(xd.grad, xr.grad)) < 2e-2
+
+
+def test_diffusion_tables_and_respacing(small):
+    _, _, _, diff = small
+    sched = O.Schedule(1000, "200")
+    assert diff.timestep_map == sched.timestep_map
+    assert np.array_equal(diff.betas, sched.betas)
+    tab = diff.coef_table_host(600.0)
+    assert tab.shape == (200, 8) and float(tab[0, 6]) == 0.0 and float(tab[5, 6]) == 1.0 and float(tab[3, 7]) == 600.0
+    assert np.allclose(tab[:, 4].numpy(), sched.posterior_log_variance_clipped.astype(np.float32))
+    from ishapediting_b200.guided_diffusion.respace import space_timesteps
+    assert space_timesteps(1000, "200") == set(sched.timestep_map)
+    assert sorted(space_timesteps(300, [10, 15, 20]))[:3] == [0, 11, 22]
+    assert len(space_timesteps(1000, "ddim50")) == 50
+
+
+def test_p_sample_guidance_api_matches_oracle(small):
+    cfg, sd, model, diff = small
+    _, x, _, noise = seeded_inputs(cfg)
+    sched = O.Schedule(1000, "200")
+    for i in (49, 0):
+        ref = O.p_sample_guidance(sd, cfg, sched, x, i, noise, feat_layer=8)
+        with torch.no_grad():
+            out = diff.p_sample_guidance(model, x, torch.tensor([i]), noise=noise, feat_layer=8)
+        assert set(out) == {"sample", "pred_xstart", "inter_feat", "model_output", "noise", "variance", "mean"}
+        for k in ("sample", "pred_xstart", "inter_feat", "model_output", "variance", "mean"):
+            assert rel_l2(out[k], ref[k]) < 1e-5, (i, k)
+        vn = torch.full_like(x, 0.25)
+        with torch.no_grad():
+            o2 = diff.p_sample_guidance(model, x, torch.tensor([i]), variance_noise=vn, feat_layer=8)
+        assert set(o2) == {"sample", "inter_feat", "variance"}
+        assert rel_l2(o2["sample"], ref["mean"] + vn) < 1e-5
+
+
+def test_ddpm_inversion_roundtrip_identity(small):
+    """gaussian_diffusion.py:525-531: img = mean + (x_i - mean) reproduces the forward chain, so the
+    final `sample` is the input x_0 (up to one fp32 rounding per step)."""
+    cfg, _, model, diff = small
+    g = torch.Generator().manual_seed(5)
+    x0 = (torch.randn(1, cfg["in_out_channels"], 32, 32, generator=g) * 0.5).clamp(-1, 1)
+    out = diff.ddpm_inversion(model, x0, 3, clip_denoised=True, feat_layer=8)
+    assert len(out["inter_feat"]) == 3 and len(out["variance_noise"]) == 3 and len(out["variance"]) == 3
+    assert float((out["sample"] - x0).abs().max()) < 1e-5
+    assert out["latent"].shape == x0.shape
+
+
+def test_align_maps_equal_resize_feat_align():
+    from ishapediting_b200.drag_utils import align_maps
+
+    for C in (512, 128, 96, 100):
+        g = torch.Generator().manual_seed(C)
+        feat = torch.randn(1, C, 5, 5, generator=g)
+        ref = O.resize_feat_align(feat)                     # (3, Ca, 5, 5)
+        chan_map, inv_map, Ca = align_maps(C)
+        assert ref.shape[1] == Ca
+        mine = feat[0][chan_map.long()].reshape(3, Ca, 5, 5)
+        assert torch.equal(mine, ref)
+        used = chan_map.long()
+        assert torch.equal(inv_map[used].long(), torch.arange(3 * Ca))
+        assert int((inv_map < 0).sum()) == C - 3 * Ca
+
+
+def test_drag_geometry_masks_are_exact_and_points_dedup():
+    """Mask index sets (drag_utils.py:322-334) bit-exact vs the full-lattice restatement; the de-duplicated
+    2-D points with multiplicity reproduce the full (2r+1)^3 grid_sample loss and gradient."""
+    from ishapediting_b200.drag_utils import DragGeometry
+
+    g = torch.Generator().manual_seed(4)
+    S, Ca, r1, voxel = 64, 170, 12, 2.0 / 256
+    src = (torch.rand(4, 3, generator=g) - 0.5).numpy()
+    tgt = src + (torch.rand(4, 3, generator=g).numpy() - 0.5) * 0.4
+    tgt[3] = [0.99, -0.98, 0.2]          # lattice partly outside [-1,1]: out-of-range indices are dropped
+    pg, sg, masks = O.drag_setup(src, tgt, r1, voxel, S)
+    geo = DragGeometry(src, tgt, r1, voxel, S, Ca)
+    assert np.array_equal(geo.mask.numpy().astype(bool), masks)
+    assert geo.mask_count == int(masks.sum())
+    for pl, idx in enumerate(geo.mask_index_sets()):
+        assert {tuple(v) for v in idx.tolist()} == {tuple(v) for v in np.argwhere(masks[pl]).tolist()}
+    assert geo.npts == 4 * 25 * 25 and float(geo.weight[0]) == 25.0
+    edit = torch.randn(3, 8, S, S, generator=g, requires_grad=True)
+    origin = torch.randn(3, 8, S, S, generator=g)
+    loss_full = O.drag_loss(edit, origin, pg, sg, masks, cof=0.2)
+    (g_full,) = torch.autograd.grad(loss_full, edit)
+    ops = RefOps("fp32")
+    chan_map = torch.arange(24, dtype=torch.int32)
+    feat = edit.detach().permute(2, 3, 0, 1).reshape(1, S, S, 24).contiguous()
+    loss, d_feat = torch.zeros(1), torch.zeros(1, S, S, 24)
+    geo8 = DragGeometry(src, tgt, r1, voxel, S, 8)
+    ops.drag_loss_grad(feat, origin.permute(0, 2, 3, 1).contiguous(), chan_map, chan_map, geo8.patch_xy, geo8.shift_xy,
+                       geo8.weight, geo8.group_size, geo8.bbox, geo8.mask, geo8.mask_count, geo8.inv_count, 0.2, 0,
+                       None, None, None, loss, d_feat)
+    assert abs(float(loss) - float(loss_full)) < 1e-5 * abs(float(loss_full))
+    assert rel_l2(d_feat.reshape(S, S, 3, 8).permute(2, 3, 0, 1), g_full) < 1e-5
+
+
+def test_guided_step_and_training_generator(small):
+    from ishapediting_b200.drag_utils import DragGeometry, DragStuff, GuidedStepper, get_args
+
+    cfg, sd, model, diff = small
+    sched = O.Schedule(1000, "200")
+    g, x, x2, noise = seeded_inputs(cfg)
+    i = 49
+    origin, src, tgt, r1, voxel, pg, sg, masks = drag_problem(cfg, sd, sched, x2, noise, i, g, r1=3, voxel=2.0 / 64)
+    ref = O.guided_step(sd, cfg, sched, x, i, origin, noise, pg, sg, masks, scale=600.0, cof=0.2)
+    geo = DragGeometry(src, tgt, r1, voxel, origin.shape[-1], origin.shape[1])
+    st = GuidedStepper(model, diff, geo, 8, 0.2, "l2", 600.0, use_graph=False)
+    st.img.copy_(x)
+    st.step(i, origin.permute(0, 2, 3, 1).contiguous(), noise)
+    assert rel_l2(st.grad, ref["grad"]) < 1e-5
+    assert rel_l2(st.img, ref["img"]) < 1e-6
+    assert abs(float(st.loss) - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
+    # DragStuff.training: generator protocol, progress values, stop flag (drag_utils.py:336-339,398)
+    a = get_args(["--num_steps", "200", "--w_time", "3", "--shape_resolution", "64"])
+    a.image_size, a.num_channels, a.attention_resolutions, a.in_out_channels = 32, 64, "8,4,2", 12
+    a.channel_mult, a.use_fp16 = "1,1,2,3,4", False
+    ds = DragStuff.__new__(DragStuff)
+    ds.args, ds.device, ds.model, ds.diffusion, ds.use_graph = a, torch.device("cpu"), model, diff, False
+    ds.r1, ds.voxel_size, ds.train_flag = 3, 2.0 / 64, True
+    ds.w = x.clone()
+    ds.feature_guidance = [origin.permute(0, 2, 3, 1).contiguous() for _ in range(3)]
+    seen = {}
+    ds.get_mesh = lambda tri_feat=None, img=None, t=0: seen.update(img=img, t=t)
+    progress = list(ds.training(src, tgt, scale=600, cof=0.2, noises=[noise] * 3))
+    assert progress == [1 - k / 2.0 for k in (2, 1, 0)] and seen["t"] == 0
+    gen = ds.training(src, tgt, scale=600, cof=0.2, noises=[noise] * 3)
+    next(gen)
+    ds.train_flag = False           # the GUI's stop button (main.py:485)
+    assert list(gen) == [] and seen["t"] == 2
