@@ -33,6 +33,7 @@ struct TcParams {
   int Cout, block_n;
   int Cin, chunks0, ntaps, chunks1;
   int k_iters, splits, stages;
+  int cluster;     // 1: the `splits` CTAs of an output tile form a thread-block cluster (DSMEM reduce)
   int tmem_cols;
   const float* bias;
   const float* residual;
@@ -142,6 +143,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16 bytes from the shared memory of CTA `rank` of this cluster, at the same offset as local address `laddr`
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t laddr, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(raddr)
+               : "memory");
+  return v;
 }
 
 // bias + residual (+ previous out) and store 8 consecutive output channels
@@ -297,7 +315,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     bool do_final = true;
     const size_t tile_id = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
-    if (p.splits > 1) {
+    if (p.cluster) {
+      // Cluster split-K: park the fp32 partial tile in this CTA's own shared memory (the pipeline
+      // buffers are free: every MMA that read them has retired); the fold happens after the cluster
+      // barrier below, through distributed shared memory.
+      do_final = false;
+      const uint32_t row_addr = tiles_addr + static_cast<uint32_t>(r) * static_cast<uint32_t>(p.block_n + 4) * 4u;
+      for (int c = 0; c < nchunks; ++c) {
+        if (cout0 + c * 32 >= p.Cout) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + static_cast<uint32_t>(c * 128 + j * 16)),
+                       "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
+      }
+    } else if (p.splits > 1) {
       // Split-K: every CTA parks its fp32 partial tile in the workspace; the LAST CTA to arrive for this
       // output tile folds all partials in split order (deterministic) and runs the real epilogue.
       float* mine = p.partial + ((tile_id * p.splits + split) * TC_BLOCK_M + r) * p.block_n;
@@ -374,6 +409,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   }
 
+  if (p.cluster) {
+    cluster_sync_all();   // every CTA of the cluster has parked its partial tile
+    if (warp >= 2) {
+      // CTA `split` folds rows [split*R, (split+1)*R) of the tile over all ranks, in rank order
+      const int et = threadIdx.x - 64;
+      const int R = TC_BLOCK_M / p.splits;
+      const int vec_per_row = p.block_n / 8;
+      const int nvec = R * vec_per_row;
+      const int per_img = p.tw * p.th;
+      for (int idx = et; idx < nvec; idx += 128) {
+        const int rr = split * R + idx / vec_per_row;
+        const int cc = (idx % vec_per_row) * 8;
+        const int col = cout0 + cc;
+        const int rn = rr / per_img;
+        const int rrem = rr - rn * per_img;
+        const int rh = rrem / p.tw;
+        const int rw = rrem - rh * p.tw;
+        if (n0 + rn >= p.N || col >= p.Cout) continue;
+        const uint32_t laddr = tiles_addr + (static_cast<uint32_t>(rr) * static_cast<uint32_t>(p.block_n + 4) +
+                                             static_cast<uint32_t>(cc)) * 4u;
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int s2 = 0; s2 < p.splits; ++s2) {
+          const float4 u0 = ld_dsmem_f4(laddr, static_cast<uint32_t>(s2));
+          const float4 u1 = ld_dsmem_f4(laddr + 16u, static_cast<uint32_t>(s2));
+          f[0] += u0.x; f[1] += u0.y; f[2] += u0.z; f[3] += u0.w;
+          f[4] += u1.x; f[5] += u1.y; f[6] += u1.z; f[7] += u1.w;
+        }
+        const size_t mm = (static_cast<size_t>(n0 + rn) * p.H + (h0 + rh)) * p.W + (w0 + rw);
+        epilogue_store8(p, f, mm * p.Cout + col, col);
+      }
+    }
+    cluster_sync_all();   // nobody leaves (and frees its shared memory) while peers still read it
+  }
+
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -430,14 +499,9 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   // at least two k-iterations; small-M layers are weight-streaming bound, so they trade a narrower
   // N tile for more CTAs pulling weights concurrently.
   const int sms = num_sms();
-  auto splits_for = [&](int tiles) {
+  auto splits_for = [&](int tiles) {   // cluster split-K: 1, 2, 4 or 8 CTAs per output tile
     int sp = 1;
-    if (tiles < sms) {
-      sp = sms / tiles;
-      if (sp > p.k_iters / 2) sp = p.k_iters / 2;
-      if (sp > 32) sp = 32;
-      if (sp < 1) sp = 1;
-    }
+    while (sp < 8 && tiles * sp * 2 <= sms && sp * 2 <= p.k_iters / 2) sp *= 2;
     return sp;
   };
   int bn = d->block_n;
@@ -460,6 +524,7 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   int splits = d->split_k ? d->split_k : splits_for(tiles);
   ISB_CHECK_ARG(splits >= 1 && splits <= p.k_iters, "conv_tc: split_k=%d out of range (k_iters=%d)", splits, p.k_iters);
   p.splits = splits;
+  p.cluster = (splits == 2 || splits == 4 || splits == 8) ? 1 : 0;   // other counts: workspace fold
   const int stage_bytes = TC_A_STAGE + bn * 128;
   const int max_stages = (TC_SMEM_LIMIT - 1024) / stage_bytes;
   int stages = d->stages;
@@ -476,9 +541,12 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   ISB_CHECK_ARG(stages >= 2, "conv_tc: not enough shared memory for 2 stages");
   p.stages = stages;
-  plan->smem_bytes = stages * stage_bytes + 1024;
+  plan->smem_bytes = stages * stage_bytes;
+  const int dump_bytes = TC_BLOCK_M * (bn + 4) * 4;   // cluster mode parks the fp32 tile in smem
+  if (p.cluster && plan->smem_bytes < dump_bytes) plan->smem_bytes = dump_bytes;
+  plan->smem_bytes += 1024;
   plan->counter_bytes = (static_cast<size_t>(mtiles) * ntiles * sizeof(int) + 255) & ~static_cast<size_t>(255);
-  plan->ws_bytes = splits > 1 ? plan->counter_bytes + static_cast<size_t>(mtiles) * ntiles * splits * TC_BLOCK_M * bn * sizeof(float) : 0;
+  plan->ws_bytes = (splits > 1 && !p.cluster) ? plan->counter_bytes + static_cast<size_t>(mtiles) * ntiles * splits * TC_BLOCK_M * bn * sizeof(float) : 0;
   plan->grid = dim3(mtiles, ntiles, splits);
   p.bias = d->bias;
   p.residual = d->residual;
@@ -545,7 +613,7 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
                     (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
                 "conv_tc: pointers must be 16-byte aligned");
   TcParams& p = plan.p;
-  if (p.splits > 1) {
+  if (p.splits > 1 && !p.cluster) {
     if (ws == nullptr || ws_bytes < plan.ws_bytes) {
       set_error("conv_tc: workspace %zu bytes < required %zu", ws_bytes, plan.ws_bytes);
       return ISB_ERR_WORKSPACE;
@@ -565,7 +633,23 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
   const int Ktot = p.ntaps * d->Cin + (d->a2 ? d->Cin2 : 0);
   rc = encode_weight_map(&mapB, d->w, d->Cout, Ktot, p.block_n);
   if (rc) return rc;
-  conv_tc_kernel<<<plan.grid, TC_THREADS, plan.smem_bytes, stream>>>(mapA, mapA2, mapB, p);
+  if (p.cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = plan.grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = p.splits;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ISB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, mapA, mapA2, mapB, p));
+  } else {
+    conv_tc_kernel<<<plan.grid, TC_THREADS, plan.smem_bytes, stream>>>(mapA, mapA2, mapB, p);
+  }
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }

@@ -15,4 +15,10 @@ CASES = [
     ("k3_32x32_128_128_split3", 1, 32, 32, 128, 128, 3, 0, True, True, False, False, {"split_k": 3}),
     ("k3_16x16_128_64_bn64_st2", 1, 16, 16, 128, 64, 3, 0, True, False, False, False, {"block_n": 64, "stages": 2}),
     ("k1_16x16_n2_192_256", 2, 16, 16, 192, 256, 1, 0, False, True, False, False, None),
+    # cluster split-K (DSMEM fold): 2, 4 and 8 CTAs per output tile, 128- and 256-wide tiles, bf16 out
+    ("k3_32x32_128_128_cl2", 1, 32, 32, 128, 128, 3, 0, True, True, False, False, {"split_k": 2}),
+    ("k3_16x16_256_256_cl4", 1, 16, 16, 256, 256, 3, 0, True, False, True, False, {"split_k": 4, "block_n": 128}),
+    ("k3_16x16_256_256_cl8_bn256", 1, 16, 16, 256, 256, 3, 0, True, True, False, False, {"split_k": 8, "block_n": 256}),
+    ("k1_8x8_1024_1024_auto", 1, 8, 8, 1024, 1024, 1, 0, True, True, False, True, None),
+    ("k3_8x8_1024_1024_auto", 1, 8, 8, 1024, 1024, 3, 0, True, False, False, False, None),
 ]
