@@ -25,6 +25,8 @@ struct BgemmParams {
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(256)
 bgemm_kernel(const BgemmParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float As[BG_BK][BG_BM + BG_PAD];
   __shared__ __align__(16) float Bs[BG_BK][BG_BN + BG_PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -132,6 +134,8 @@ __device__ __forceinline__ void tg_load_tile(const float* __restrict__ src, int 
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(128)
 bgemm_mma_kernel(const BgemmParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) __nv_bfloat16 As[TG_BM][TG_LD];
   __shared__ __align__(16) __nv_bfloat16 Bs[TG_BN][TG_LD];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -198,7 +202,7 @@ template <bool A_K, bool B_K>
 static int bgemm_mma(const BgemmParams& p, int batches, cudaStream_t st) {
   ISB_CHECK_ARG(p.M % TG_BM == 0 && p.N % TG_BN == 0 && p.K % TG_BK == 0, "attention gemm (mma): M=%d N=%d K=%d must be multiples of 64/64/32", p.M, p.N, p.K);
   dim3 grid(p.M / TG_BM, p.N / TG_BN, batches);
-  bgemm_mma_kernel<A_K, B_K><<<grid, 128, 0, st>>>(p);
+  ISB_CUDA(isb::launch(bgemm_mma_kernel<A_K, B_K>, grid, 128, 0, st, p));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }
@@ -207,7 +211,7 @@ template <bool A_K, bool B_K>
 static int bgemm(const BgemmParams& p, int batches, cudaStream_t st) {
   ISB_CHECK_ARG(p.M % BG_BM == 0 && p.N % BG_BN == 0 && p.K % BG_BK == 0, "attention gemm: M=%d N=%d K=%d must be multiples of 64/64/16", p.M, p.N, p.K);
   dim3 grid(p.M / BG_BM, p.N / BG_BN, batches);
-  bgemm_kernel<A_K, B_K><<<grid, 256, 0, st>>>(p);
+  ISB_CUDA(isb::launch(bgemm_kernel<A_K, B_K>, grid, 256, 0, st, p));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }
@@ -220,6 +224,8 @@ static int bgemm_any(const BgemmParams& p, int batches, bool tensor_cores, cudaS
 // one block (128 threads) per row of length T: in-place fp32 softmax (unet.py:352)
 __global__ void __launch_bounds__(128)
 softmax_rows_kernel(float* __restrict__ s, int T) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[4];
   float* row = s + static_cast<size_t>(blockIdx.x) * T;
   const int tid = threadIdx.x;
@@ -259,6 +265,8 @@ softmax_rows_kernel(float* __restrict__ s, int T) {
 // dS = alpha * P * (dP - sum_s dP*P), in place on dp
 __global__ void __launch_bounds__(128)
 softmax_bwd_rows_kernel(const float* __restrict__ probs, float* __restrict__ dp, int T, float alpha) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[4];
   const float* prow = probs + static_cast<size_t>(blockIdx.x) * T;
   float* drow = dp + static_cast<size_t>(blockIdx.x) * T;
@@ -306,7 +314,7 @@ int isb_attention_forward(const float* qkv, int N, int T, int heads, int ch, flo
   const bool tc = out_dtype == ISB_BF16;   // bf16 mode -> tensor cores; fp32 mode -> FFMA
   int rc = isb::bgemm_any<true, true>(p, N * heads, tc, st);
   if (rc) return rc;
-  isb::softmax_rows_kernel<<<N * heads * T, 128, 0, st>>>(probs, T);
+  ISB_CUDA(isb::launch(isb::softmax_rows_kernel, N * heads * T, 128, 0, st, probs, T));
   ISB_LAUNCH_CHECK();
   // O = P V
   p.A = probs; p.B = qkv + 2 * ch; p.C = out;
@@ -353,7 +361,7 @@ int isb_attention_backward(const float* qkv, const float* probs, const float* d_
   p.alpha = 1.0f; p.c_dtype = ISB_F32;
   rc = isb::bgemm_any<true, true>(p, N * heads, tc, st);
   if (rc) return rc;
-  isb::softmax_bwd_rows_kernel<<<N * heads * T, 128, 0, st>>>(probs, tmp, T, alpha);
+  ISB_CUDA(isb::launch(isb::softmax_bwd_rows_kernel, N * heads * T, 128, 0, st, probs, tmp, T, alpha));
   ISB_LAUNCH_CHECK();
   // dQ[t,c] = sum_s dS[t,s] K[s,c]
   p.A = tmp; p.B = qkv + ch; p.C = dq;

@@ -59,6 +59,32 @@ tensormap_encode_fn get_tensormap_encode();
 // ---- device helpers -------------------------------------------------------
 #ifdef __CUDACC__
 
+// Programmatic dependent launch (PDL).  Every kernel of this library is launched with
+// programmaticStreamSerialization: it may be scheduled while its predecessor in the stream is
+// still draining, runs its input-independent prologue, and blocks in pdl_wait() until the
+// predecessor has completed and flushed.  pdl_trigger() (first statement of every kernel) lets the
+// successor start that early.  Rule: no global read of produced data and NO global write before
+// pdl_wait().  ISB_PDL=0 in the environment turns the attribute off (plain stream order).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float silu_f(float z) { return z / (1.0f + __expf(-z)); }
 // d silu / dz = s * (1 + z * (1 - s)),  s = sigmoid(z)
 __device__ __forceinline__ float silu_grad_f(float z) {

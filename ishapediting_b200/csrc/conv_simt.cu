@@ -20,6 +20,8 @@ struct SimtParams {
 
 __global__ void __launch_bounds__(256)
 conv_simt_kernel(const SimtParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float As[SM_BK][SM_BM + SM_PAD];
   __shared__ float Bs[SM_BK][SM_BN + SM_PAD];
   const int tid = threadIdx.x;
@@ -132,7 +134,7 @@ static int conv_simt_launch(const isb_conv_desc* d, cudaStream_t stream) {
   p.Ktot = d->ksize * d->ksize * d->Cin + p.Cin2;
   p.M = static_cast<long long>(d->N) * d->H * d->W;
   dim3 grid(cdiv(p.M, SM_BM), cdiv(d->Cout, SM_BN));
-  conv_simt_kernel<<<grid, 256, 0, stream>>>(p);
+  ISB_CUDA(isb::launch(conv_simt_kernel, grid, 256, 0, stream, p));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }

@@ -189,6 +189,7 @@ __device__ __forceinline__ void epilogue_store8(const TcParams& p, float* f, siz
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  pdl_trigger();   // let the next kernel's prologue overlap this kernel (it blocks in its own pdl_wait)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
@@ -244,15 +245,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ===== TMA producer =====
     if (lane == 0) {
       const int seg0_iters = p.ntaps * p.chunks0;
-      for (int it = k_begin; it < k_end; ++it) {
-        const int i = it - k_begin;
+      const int niter = k_end - k_begin;
+      const int npre = niter < p.stages ? niter : p.stages;
+      auto load_b = [&](int i) {
+        const int it = k_begin + i;
         const int s = i % p.stages;
-        const uint32_t ph = static_cast<uint32_t>(i / p.stages) & 1u;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_expect_tx(fb, stage_bytes);
+        const uint32_t b_dst = tiles_addr + static_cast<uint32_t>(s) * stage_bytes + TC_A_STAGE;
+        int kcoord;
+        if (it < seg0_iters) {
+          const int tap = it / p.chunks0;
+          kcoord = tap * p.Cin + (it - tap * p.chunks0) * TC_BLOCK_K;
+        } else {
+          kcoord = p.ntaps * p.Cin + (it - seg0_iters) * TC_BLOCK_K;
+        }
+        tma_load_2d(b_dst, &mapB, smem_u32(&full_bar[s]), kcoord, cout0);
+      };
+      auto load_a = [&](int i) {
+        const int it = k_begin + i;
+        const int s = i % p.stages;
         const uint32_t a_dst = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
-        const uint32_t b_dst = a_dst + TC_A_STAGE;
+        const uint32_t fb = smem_u32(&full_bar[s]);
         if (it < seg0_iters) {
           const int tap = it / p.chunks0;
           const int chunk = it - tap * p.chunks0;
@@ -262,12 +274,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             dw = tap % 3 - 1;
           }
           tma_load_4d(a_dst, &mapA, fb, chunk * TC_BLOCK_K, w0 + dw, h0 + dh, n0);
-          tma_load_2d(b_dst, &mapB, fb, tap * p.Cin + chunk * TC_BLOCK_K, cout0);
         } else {
-          const int chunk = it - seg0_iters;
-          tma_load_4d(a_dst, &mapA2, fb, chunk * TC_BLOCK_K, w0, h0, n0);
-          tma_load_2d(b_dst, &mapB, fb, p.ntaps * p.Cin + chunk * TC_BLOCK_K, cout0);
+          tma_load_4d(a_dst, &mapA2, fb, (it - seg0_iters) * TC_BLOCK_K, w0, h0, n0);
         }
+      };
+      // The weight panels never change during a step: start streaming them into the ring before the
+      // producer of our activations has even finished (PDL), then wait and fetch the activations.
+      for (int i = 0; i < npre; ++i) {
+        mbar_expect_tx(smem_u32(&full_bar[i]), stage_bytes);
+        load_b(i);
+      }
+      pdl_wait();
+      for (int i = 0; i < npre; ++i) load_a(i);
+      for (int i = npre; i < niter; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = static_cast<uint32_t>(i / p.stages) & 1u;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        mbar_expect_tx(smem_u32(&full_bar[s]), stage_bytes);
+        load_a(i);
+        load_b(i);
       }
     }
   } else if (warp == 1) {
@@ -312,6 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tc_fence_after();
+    pdl_wait();   // residual / accumulate reads and every global write come after the predecessor
 
     bool do_final = true;
     const size_t tile_id = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
@@ -633,23 +659,28 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
   const int Ktot = p.ntaps * d->Cin + (d->a2 ? d->Cin2 : 0);
   rc = encode_weight_map(&mapB, d->w, d->Cout, Ktot, p.block_n);
   if (rc) return rc;
-  if (p.cluster) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = plan.grid;
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = plan.smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = p.splits;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    ISB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, mapA, mapA2, mapB, p));
-  } else {
-    conv_tc_kernel<<<plan.grid, TC_THREADS, plan.smem_bytes, stream>>>(mapA, mapA2, mapB, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = plan.grid;
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = plan.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
+  if (p.cluster) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = p.splits;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  ISB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, mapA, mapA2, mapB, p));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }

@@ -20,6 +20,8 @@ struct DdpmArgs {
 // block: 32 pixels x 32 channels; grid (HW/32, C/32, N)
 __global__ void __launch_bounds__(256)
 ddpm_step_kernel(const DdpmArgs a) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float t_eps[32][33];
   __shared__ float t_v[32][33];
   const int n = blockIdx.z;
@@ -85,7 +87,7 @@ int isb_ddpm_step(const isb_ddpm_desc* d, isb_stream_t stream) {
                   d->C, d->H * d->W, d->clip_denoised,
                   d->x_next, d->sample, d->mean, d->var, d->x0, d->eps};
   dim3 grid(isb::cdiv(a.HW, 32), isb::cdiv(a.C, 32), d->N);
-  isb::ddpm_step_kernel<<<grid, 256, 0, isb::as_stream(stream)>>>(a);
+  ISB_CUDA(isb::launch(isb::ddpm_step_kernel, grid, 256, 0, isb::as_stream(stream), a));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }

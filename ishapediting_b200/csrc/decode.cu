@@ -90,6 +90,8 @@ __device__ __forceinline__ void mlp_layer(const float (*Wt)[DC_H], const float* 
 template <bool GRID>
 __global__ void __launch_bounds__(DC_THREADS, 1)
 triplane_decode_kernel(const DecodeArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t dsm_raw[];
   DecodeSmem& s = *reinterpret_cast<DecodeSmem*>(dsm_raw);
   const int tid = threadIdx.x;
@@ -186,8 +188,8 @@ static int decode_launch(const DecodeArgs& a, bool grid_mode, cudaStream_t st) {
   long long blocks = ntiles < num_sms() ? ntiles : num_sms();
   if (blocks < 1) return ISB_OK;
   const size_t smem = sizeof(DecodeSmem);
-  if (grid_mode) triplane_decode_kernel<true><<<static_cast<int>(blocks), DC_THREADS, smem, st>>>(a);
-  else triplane_decode_kernel<false><<<static_cast<int>(blocks), DC_THREADS, smem, st>>>(a);
+  if (grid_mode) ISB_CUDA(isb::launch(triplane_decode_kernel<true>, static_cast<int>(blocks), DC_THREADS, smem, st, a));
+  else ISB_CUDA(isb::launch(triplane_decode_kernel<false>, static_cast<int>(blocks), DC_THREADS, smem, st, a));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }

@@ -49,6 +49,8 @@ __device__ __forceinline__ Bilin bilin_setup(float gx, float gy, int S) {
 // grid (npts, 3); block loops over the Ca aligned channels
 __global__ void __launch_bounds__(192)
 drag_sample_kernel(const DragArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int j = blockIdx.x, pl = blockIdx.y;
   const int S = a.S;
   const size_t pj = static_cast<size_t>(pl) * a.npts + j;
@@ -102,6 +104,8 @@ drag_sample_kernel(const DragArgs a) {
 // one thread per (pixel, feature channel)
 __global__ void __launch_bounds__(256)
 drag_gather_kernel(const DragArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int S = a.S;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(S) * S * a.Cf;
@@ -154,6 +158,8 @@ drag_gather_kernel(const DragArgs a) {
 
 __global__ void __launch_bounds__(256)
 drag_loss_kernel(const DragArgs a) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double red[2][8];
   double motion = 0, mask = 0;
   const int n_motion = 3 * a.npts;
@@ -175,6 +181,8 @@ drag_loss_kernel(const DragArgs a) {
 __global__ void __launch_bounds__(256)
 resize_feat_align_kernel(const float* __restrict__ feat, int S, int Cf, const int32_t* __restrict__ chan_map,
                          float* __restrict__ out, int Ca) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = 3LL * S * S * Ca;
   if (idx >= total) return;
@@ -209,11 +217,11 @@ int isb_drag_loss_grad(const isb_drag_desc* d, isb_stream_t stream) {
                   d->bbox, d->mask, d->mask_count, d->inv_count, d->cof, d->loss_type,
                   d->g, d->pt_info, d->partial, gblocks, d->loss, d->d_feat};
   cudaStream_t st = isb::as_stream(stream);
-  isb::drag_sample_kernel<<<dim3(d->npts, 3), 192, 0, st>>>(a);
+  ISB_CUDA(isb::launch(isb::drag_sample_kernel, dim3(d->npts, 3), 192, 0, st, a));
   ISB_LAUNCH_CHECK();
-  isb::drag_gather_kernel<<<gblocks, 256, 0, st>>>(a);
+  ISB_CUDA(isb::launch(isb::drag_gather_kernel, gblocks, 256, 0, st, a));
   ISB_LAUNCH_CHECK();
-  isb::drag_loss_kernel<<<1, 256, 0, st>>>(a);
+  ISB_CUDA(isb::launch(isb::drag_loss_kernel, 1, 256, 0, st, a));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }
@@ -222,7 +230,7 @@ int isb_resize_feat_align(const float* feat, int S, int Cf, const int32_t* chan_
                           isb_stream_t stream) {
   ISB_CHECK_ARG(feat && chan_map && out && S > 0 && Cf > 0 && Ca > 0, "isb_resize_feat_align: bad args");
   const long long total = 3LL * S * S * Ca;
-  isb::resize_feat_align_kernel<<<isb::cdiv(total, 256), 256, 0, isb::as_stream(stream)>>>(feat, S, Cf, chan_map, out, Ca);
+  ISB_CUDA(isb::launch(isb::resize_feat_align_kernel, isb::cdiv(total, 256), 256, 0, isb::as_stream(stream), feat, S, Cf, chan_map, out, Ca));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }

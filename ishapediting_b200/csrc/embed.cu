@@ -10,6 +10,8 @@ namespace isb {
 // (computed with the reference's own expression so the table is bit-identical).
 __global__ void sinusoid_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs, int N, int half,
                                 float* __restrict__ emb) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * half) return;
   const int n = idx / half, i = idx % half;
@@ -22,6 +24,8 @@ __global__ void sinusoid_kernel(const int64_t* __restrict__ t, const float* __re
 __global__ void __launch_bounds__(256)
 gemv_rows_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ in,
                  float* __restrict__ out, int R, int K, int N, int silu_out) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
   const int lane = threadIdx.x & 31;
@@ -58,14 +62,14 @@ int isb_time_embed(const int64_t* t, const float* freqs, int N, int model_ch, in
   float* h1 = emb + static_cast<size_t>(N) * model_ch;   // [N, hidden]
   float* h2 = h1 + static_cast<size_t>(N) * hidden;      // [N, hidden] = silu(time_embed(emb))
   const int half = model_ch / 2;
-  isb::sinusoid_kernel<<<isb::cdiv(N * half, 128), 128, 0, st>>>(t, freqs, N, half, emb);
+  ISB_CUDA(isb::launch(isb::sinusoid_kernel, isb::cdiv(N * half, 128), 128, 0, st, t, freqs, N, half, emb));
   ISB_LAUNCH_CHECK();
-  isb::gemv_rows_kernel<<<isb::cdiv(hidden, 8), 256, 0, st>>>(w1, b1, emb, h1, hidden, model_ch, N, 1);
+  ISB_CUDA(isb::launch(isb::gemv_rows_kernel, isb::cdiv(hidden, 8), 256, 0, st, w1, b1, emb, h1, hidden, model_ch, N, 1));
   ISB_LAUNCH_CHECK();
   // every consumer applies SiLU first (unet.py:200), so store silu(emb) directly
-  isb::gemv_rows_kernel<<<isb::cdiv(hidden, 8), 256, 0, st>>>(w2, b2, h1, h2, hidden, hidden, N, 1);
+  ISB_CUDA(isb::launch(isb::gemv_rows_kernel, isb::cdiv(hidden, 8), 256, 0, st, w2, b2, h1, h2, hidden, hidden, N, 1));
   ISB_LAUNCH_CHECK();
-  isb::gemv_rows_kernel<<<isb::cdiv(rows_all, 8), 256, 0, st>>>(w_all, b_all, h2, film_all, rows_all, hidden, N, 0);
+  ISB_CUDA(isb::launch(isb::gemv_rows_kernel, isb::cdiv(rows_all, 8), 256, 0, st, w_all, b_all, h2, film_all, rows_all, hidden, N, 0));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }

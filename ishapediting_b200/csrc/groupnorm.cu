@@ -82,6 +82,8 @@ __device__ __forceinline__ bool gn_block_reduce_and_fold(const GnArgs& a, int ng
 // grid (splits, G, N)
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const GnArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int split = blockIdx.x, g = blockIdx.y, n = blockIdx.z;
   const int V = a.Cg / 8;
   const long long total = static_cast<long long>(a.HW) * V;
@@ -124,6 +126,8 @@ __device__ __forceinline__ void gn_act8(const GnArgs& a, const float* x, float m
 
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const GnArgs a, const GnFwdOut o) {
+  pdl_trigger();
+  pdl_wait();
   const int CV = a.C / 8;
   const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;  // thread grid
   const long long total = static_cast<long long>(a.N) * Ho * Wo * CV;
@@ -237,6 +241,8 @@ __device__ __forceinline__ void gn_bwd_terms8(const GnArgs& a, const GnBwdArgs& 
 
 __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const GnArgs a, const GnBwdArgs b) {
+  pdl_trigger();
+  pdl_wait();
   const int split = blockIdx.x, g = blockIdx.y, n = blockIdx.z;
   const int V = a.Cg / 8;
   const long long total = static_cast<long long>(a.HW) * V;
@@ -261,6 +267,8 @@ gn_bwd_reduce_kernel(const GnArgs a, const GnBwdArgs b) {
 
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const GnArgs a, const GnBwdArgs b) {
+  pdl_trigger();
+  pdl_wait();
   const int CV = a.C / 8;
   const long long total = static_cast<long long>(a.N) * a.HW * CV;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -358,12 +366,12 @@ int isb_gn_forward(const isb_gn_desc* d, void* scratch, isb_stream_t stream) {
   if (rc) return rc;
   ISB_CHECK_ARG(d->y != nullptr, "isb_gn_forward: y missing");
   cudaStream_t st = isb::as_stream(stream);
-  isb::gn_stats_kernel<<<dim3(a.splits, a.groups, a.N), 256, 0, st>>>(a);
+  ISB_CUDA(isb::launch(isb::gn_stats_kernel, dim3(a.splits, a.groups, a.N), 256, 0, st, a));
   ISB_LAUNCH_CHECK();
   isb::GnFwdOut o{d->y, d->y_dtype, d->raw, d->raw_dtype, d->xres};
   const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;
   const long long total = static_cast<long long>(a.N) * Ho * Wo * (a.C / 8);
-  isb::gn_apply_kernel<<<isb::cdiv(total, 256), 256, 0, st>>>(a, o);
+  ISB_CUDA(isb::launch(isb::gn_apply_kernel, isb::cdiv(total, 256), 256, 0, st, a, o));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }
@@ -378,10 +386,10 @@ int isb_gn_backward(const isb_gn_bwd_desc* d, void* scratch, isb_stream_t stream
   isb::GnBwdArgs b{d->dy, d->gres, d->gres_at_input, d->gx1, d->acc1, d->gx1_lo,
                    d->gx2, d->acc2, d->gx2_lo, d->lo_dtype};
   cudaStream_t st = isb::as_stream(stream);
-  isb::gn_bwd_reduce_kernel<<<dim3(a.splits, a.groups, a.N), 256, 0, st>>>(a, b);
+  ISB_CUDA(isb::launch(isb::gn_bwd_reduce_kernel, dim3(a.splits, a.groups, a.N), 256, 0, st, a, b));
   ISB_LAUNCH_CHECK();
   const long long total = static_cast<long long>(a.N) * a.HW * (a.C / 8);
-  isb::gn_bwd_apply_kernel<<<isb::cdiv(total, 256), 256, 0, st>>>(a, b);
+  ISB_CUDA(isb::launch(isb::gn_bwd_apply_kernel, isb::cdiv(total, 256), 256, 0, st, a, b));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }

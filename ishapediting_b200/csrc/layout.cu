@@ -9,6 +9,8 @@ namespace isb {
 template <typename TOut>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int C, int HW, int c_pad) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -35,6 +37,8 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int C
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const TIn* __restrict__ src, float* __restrict__ dst, int C, int HW, int c_stride) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -59,6 +63,8 @@ nhwc_to_nchw_kernel(const TIn* __restrict__ src, float* __restrict__ dst, int C,
 
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n8) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   float v[8];
@@ -76,10 +82,9 @@ int isb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, i
   const int HW = H * W;
   dim3 grid(isb::cdiv(HW, 32), isb::cdiv(c_pad, 32), N);
   if (dst_dtype == ISB_BF16)
-    isb::nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, isb::as_stream(stream)>>>(
-        src, static_cast<__nv_bfloat16*>(dst), C, HW, c_pad);
+    ISB_CUDA(isb::launch(isb::nchw_to_nhwc_kernel<__nv_bfloat16>, grid, 256, 0, isb::as_stream(stream), src, static_cast<__nv_bfloat16*>(dst), C, HW, c_pad));
   else if (dst_dtype == ISB_F32)
-    isb::nchw_to_nhwc_kernel<float><<<grid, 256, 0, isb::as_stream(stream)>>>(src, static_cast<float*>(dst), C, HW, c_pad);
+    ISB_CUDA(isb::launch(isb::nchw_to_nhwc_kernel<float>, grid, 256, 0, isb::as_stream(stream), src, static_cast<float*>(dst), C, HW, c_pad));
   else ISB_CHECK_ARG(false, "isb_nchw_to_nhwc: bad dtype");
   ISB_LAUNCH_CHECK();
   return ISB_OK;
@@ -91,10 +96,9 @@ int isb_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int N, int C, i
   const int HW = H * W;
   dim3 grid(isb::cdiv(HW, 32), isb::cdiv(C, 32), N);
   if (src_dtype == ISB_BF16)
-    isb::nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, isb::as_stream(stream)>>>(
-        static_cast<const __nv_bfloat16*>(src), dst, C, HW, c_stride);
+    ISB_CUDA(isb::launch(isb::nhwc_to_nchw_kernel<__nv_bfloat16>, grid, 256, 0, isb::as_stream(stream), static_cast<const __nv_bfloat16*>(src), dst, C, HW, c_stride));
   else if (src_dtype == ISB_F32)
-    isb::nhwc_to_nchw_kernel<float><<<grid, 256, 0, isb::as_stream(stream)>>>(static_cast<const float*>(src), dst, C, HW, c_stride);
+    ISB_CUDA(isb::launch(isb::nhwc_to_nchw_kernel<float>, grid, 256, 0, isb::as_stream(stream), static_cast<const float*>(src), dst, C, HW, c_stride));
   else ISB_CHECK_ARG(false, "isb_nhwc_to_nchw: bad dtype");
   ISB_LAUNCH_CHECK();
   return ISB_OK;
@@ -104,8 +108,7 @@ int isb_cast_f32_bf16(const float* src, void* dst, size_t n, isb_stream_t stream
   ISB_CHECK_ARG(src && dst && n % 8 == 0, "isb_cast_f32_bf16: n must be a multiple of 8");
   if (n == 0) return ISB_OK;
   const size_t n8 = n / 8;
-  isb::cast_f32_bf16_kernel<<<isb::cdiv(n8, 256), 256, 0, isb::as_stream(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst), n8);
+  ISB_CUDA(isb::launch(isb::cast_f32_bf16_kernel, isb::cdiv(n8, 256), 256, 0, isb::as_stream(stream), src, static_cast<__nv_bfloat16*>(dst), n8));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }

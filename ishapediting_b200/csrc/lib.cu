@@ -1,6 +1,7 @@
 // lib.cu — library state: init, error string, launch counter.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 #include "common.cuh"
 
@@ -20,6 +21,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 bool is_initialised() { return g_init.load(); }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ISB_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 int num_sms() { return g_num_sms; }
 tensormap_encode_fn get_tensormap_encode() { return g_encode; }
 
