@@ -77,7 +77,8 @@ typedef struct isb_conv_desc {
   int ksize;             /* 1 or 3 (stride 1, zero pad ksize/2) */
   const void* a2;        /* optional second 1x1 source [N,H,W,Cin2] or NULL */
   int Cin2;
-  const void* w;         /* packed [Cout][ksize*ksize*Cin + Cin2], a_dtype */
+  const void* w;         /* packed [Cout][K], K = ksize*ksize*Cin + Cin2, a_dtype; or, if w_tiled,
+                            the same matrix as [Cout/64][K/64][64][64] panels (bf16 path only) */
   const float* bias;     /* [Cout] or NULL */
   const float* residual; /* fp32 [N,H,W,Cout] or NULL */
   void* out;             /* [N,H,W,Cout] */
@@ -88,6 +89,7 @@ typedef struct isb_conv_desc {
   int block_n;           /* 64,128,192,256 */
   int split_k;
   int stages;
+  int w_tiled;           /* 1: w is panel-tiled (see above); needs Cout % 64 == 0 */
 } isb_conv_desc;
 /* Workspace (split-K partial tiles + arrival counters): must be ZERO-FILLED by the caller before its
  * first use; every launch leaves the counters at zero again, so one buffer serves all layers. */

@@ -33,6 +33,7 @@ struct TcParams {
   int Cout, block_n;
   int Cin, chunks0, ntaps, chunks1;
   int k_iters, splits, stages;
+  int w_tiled;     // 1: weights packed as [Cout/64][K/64][64][64] panels (8 KiB contiguous per TMA box row-group)
   int cluster;     // 1: the `splits` CTAs of an output tile form a thread-block cluster (DSMEM reduce)
   int tmem_cols;
   const float* bias;
@@ -258,7 +259,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else {
           kcoord = p.ntaps * p.Cin + (it - seg0_iters) * TC_BLOCK_K;
         }
-        tma_load_2d(b_dst, &mapB, smem_u32(&full_bar[s]), kcoord, cout0);
+        if (p.w_tiled) tma_load_4d(b_dst, &mapB, smem_u32(&full_bar[s]), 0, 0, kcoord / TC_BLOCK_K, cout0 / 64);
+        else tma_load_2d(b_dst, &mapB, smem_u32(&full_bar[s]), kcoord, cout0);
       };
       auto load_a = [&](int i) {
         const int it = k_begin + i;
@@ -581,6 +583,7 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   p.accumulate = d->accumulate;
   p.partial = nullptr;
   p.counters = nullptr;
+  p.w_tiled = d->w_tiled;
   return ISB_OK;
 }
 
@@ -613,6 +616,26 @@ static int encode_weight_map(CUtensorMap* m, const void* ptr, int Cout, int Ktot
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(weight %dx%d, box 64x%d) failed: %d", Cout, Ktot, bn, (int)r);
+    return ISB_ERR_CUDA;
+  }
+  return ISB_OK;
+}
+
+// Panel-tiled weights: [Cout/64][K/64][64 rows][64 k]; a box {64,64,1,bn/64} lands in shared memory exactly
+// like the 2-D box {64,bn} of the row-major layout, but every 64x64 panel is one contiguous 8 KiB read and
+// consecutive k-chunks of a 64-row group are adjacent in memory -> the K loop streams HBM sequentially.
+static int encode_weight_map_tiled(CUtensorMap* m, const void* ptr, int Cout, int Ktot, int bn) {
+  const cuuint64_t kc = (cuuint64_t)Ktot / 64, groups = (cuuint64_t)Cout / 64;
+  cuuint64_t gdim[4] = {64, 64, kc, groups};
+  cuuint64_t gstr[3] = {128, 8192, kc * 8192};
+  cuuint32_t box[4] = {64, 64, 1, (cuuint32_t)(bn / 64)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_tensormap_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim,
+                                      gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(tiled weight %dx%d, bn %d) failed: %d", Cout, Ktot, bn, (int)r);
     return ISB_ERR_CUDA;
   }
   return ISB_OK;
@@ -657,7 +680,12 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
     mapA2 = mapA;
   }
   const int Ktot = p.ntaps * d->Cin + (d->a2 ? d->Cin2 : 0);
-  rc = encode_weight_map(&mapB, d->w, d->Cout, Ktot, p.block_n);
+  if (d->w_tiled) {
+    ISB_CHECK_ARG(d->Cout % 64 == 0 && p.block_n % 64 == 0, "conv_tc: panel-tiled weights need Cout %% 64 == 0 and block_n %% 64 == 0 (Cout=%d, block_n=%d)", d->Cout, p.block_n);
+    rc = encode_weight_map_tiled(&mapB, d->w, d->Cout, Ktot, p.block_n);
+  } else {
+    rc = encode_weight_map(&mapB, d->w, d->Cout, Ktot, p.block_n);
+  }
   if (rc) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = plan.grid;

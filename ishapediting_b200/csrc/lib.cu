@@ -24,7 +24,7 @@ bool is_initialised() { return g_init.load(); }
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("ISB_PDL");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';   // measured neutral under CUDA-graph replay (profiles/): opt-in
   }();
   return on;
 }

@@ -157,17 +157,17 @@ class _ResLayer:
         gn2, conv2 = mod.out_layers[0], mod.out_layers[3]
         self.g1, self.be1 = _f32(gn1.weight), _f32(gn1.bias)
         self.g2, self.be2 = _f32(gn2.weight), _f32(gn2.bias)
-        self.w1, self.b1 = _pack3(conv1.weight, lo), _f32(conv1.bias)
+        self.w1, self.b1 = ops.pack_weight(_pack3(conv1.weight, lo)), _f32(conv1.bias)
         w2 = _pack3(conv2.weight, lo)
         b2 = _f32(conv2.bias)
         if self.has_skip_conv:
             w2 = th.cat([w2, _pack1(mod.skip_connection.weight, lo)], dim=1).contiguous()
             b2 = (b2 + _f32(mod.skip_connection.bias)).contiguous()
-        self.w2, self.b2 = w2, b2
+        self.w2, self.b2 = ops.pack_weight(w2), b2
         if plan.want_backward:
-            self.w1_d = _pack3_dgrad(conv1.weight, lo)
-            self.w2_d = _pack3_dgrad(conv2.weight, lo)
-            self.wskip_d = _pack1_dgrad(mod.skip_connection.weight, lo) if self.has_skip_conv else None
+            self.w1_d = ops.pack_weight(_pack3_dgrad(conv1.weight, lo))
+            self.w2_d = ops.pack_weight(_pack3_dgrad(conv2.weight, lo))
+            self.wskip_d = ops.pack_weight(_pack1_dgrad(mod.skip_connection.weight, lo)) if self.has_skip_conv else None
         # buffers
         self.stats1, self.stats2 = ops.empty((N, 32, 2)), ops.empty((N, 32, 2))
         self.a1 = plan.scratch("a", (N, Ho, Wo, Cin), lo)
@@ -231,11 +231,11 @@ class _AttnLayer:
         assert Cc == mod.channels
         self.heads = mod.num_heads
         self.g, self.be = _f32(mod.norm.weight), _f32(mod.norm.bias)
-        self.wqkv, self.bqkv = _pack1(mod.qkv.weight, lo), _f32(mod.qkv.bias)
-        self.wproj, self.bproj = _pack1(mod.proj_out.weight, lo), _f32(mod.proj_out.bias)
+        self.wqkv, self.bqkv = ops.pack_weight(_pack1(mod.qkv.weight, lo)), _f32(mod.qkv.bias)
+        self.wproj, self.bproj = ops.pack_weight(_pack1(mod.proj_out.weight, lo)), _f32(mod.proj_out.bias)
         if plan.want_backward:
-            self.wqkv_d = _pack1_dgrad(mod.qkv.weight, lo)
-            self.wproj_d = _pack1_dgrad(mod.proj_out.weight, lo)
+            self.wqkv_d = ops.pack_weight(_pack1_dgrad(mod.qkv.weight, lo))
+            self.wproj_d = ops.pack_weight(_pack1_dgrad(mod.proj_out.weight, lo))
         T = H * W
         self.stats = ops.empty((N, 32, 2))
         self.a = plan.scratch("a", (N, H, W, Cc), lo)
@@ -306,9 +306,9 @@ class _Plan:
         conv0 = model.input_blocks[0][0]
         w0 = th.zeros(conv0.weight.shape[0], self.cin_pad, 3, 3, device=conv0.weight.device)
         w0[:, :Cin] = conv0.weight.detach()
-        self.w_in, self.b_in = _pack3(w0, lo), _f32(conv0.bias)
+        self.w_in, self.b_in = ops.pack_weight(_pack3(w0, lo)), _f32(conv0.bias)
         if want_backward:
-            self.w_in_d = _pack3_dgrad(w0, lo)
+            self.w_in_d = ops.pack_weight(_pack3_dgrad(w0, lo))
         self.x_nchw = ops.empty((N, Cin, H, W))
         self.x_lo = ops.empty((N, H, W, self.cin_pad), lo)
         self.h0 = _T(ops.empty((N, H, W, conv0.weight.shape[0])), "input_blocks.0")
@@ -343,9 +343,9 @@ class _Plan:
         # --- out (unet.py:612-616) ---
         gn, conv = model.out[0], model.out[2]
         self.out_g, self.out_b = _f32(gn.weight), _f32(gn.bias)
-        self.w_out, self.b_out = _pack3(conv.weight, lo), _f32(conv.bias)
+        self.w_out, self.b_out = ops.pack_weight(_pack3(conv.weight, lo)), _f32(conv.bias)
         if want_backward:
-            self.w_out_d = _pack3_dgrad(conv.weight, lo)
+            self.w_out_d = ops.pack_weight(_pack3_dgrad(conv.weight, lo))
         self.out_stats = ops.empty((N, 32, 2))
         self.out_a = self.scratch("a", (N, H, W, h.val.shape[3]), lo)
         self.out_nhwc = ops.empty((N, H, W, conv.weight.shape[0]))

@@ -32,6 +32,14 @@ def _chk(t, dtype=None):
     return t
 
 
+class PackedWeight:
+    """A GEMM weight panel in the backend's preferred memory layout (see CudaOps.pack_weight)."""
+    __slots__ = ("data", "cout", "k", "tiled")
+
+    def __init__(self, data, cout, k, tiled):
+        self.data, self.cout, self.k, self.tiled = data, cout, k, tiled
+
+
 class CudaOps:
     name = "cuda"
 
@@ -97,8 +105,24 @@ class CudaOps:
         return dst
 
     # ---- conv / linear --------------------------------------------------------
+    def pack_weight(self, w2d):
+        """[Cout, K] row-major -> the layout the conv kernel streams best.  bf16 mode with Cout, K multiples
+        of 64: 64x64 panels, [Cout/64][K/64][64][64], so that every TMA box is a run of contiguous 8 KiB
+        blocks and the K loop walks HBM sequentially (the row-major layout scatters each box over `bn`
+        rows that are K*2 bytes apart)."""
+        cout, k = w2d.shape
+        if self.mode == "bf16" and cout % 64 == 0 and k % 64 == 0:
+            t = w2d.reshape(cout // 64, 64, k // 64, 64).permute(0, 2, 1, 3).contiguous()
+            return PackedWeight(t, cout, k, True)
+        return PackedWeight(w2d.contiguous(), cout, k, False)
+
     def conv(self, a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None):
-        """a [N,H,W,Cin], w packed [Cout, k*k*Cin (+Cin2)], out [N,H,W,Cout]."""
+        """a [N,H,W,Cin], w PackedWeight (or a plain [Cout, k*k*Cin (+Cin2)] tensor), out [N,H,W,Cout]."""
+        tiled = False
+        if isinstance(w, PackedWeight):
+            wshape, tiled, w = (w.cout, w.k), w.tiled, w.data
+        else:
+            wshape = tuple(w.shape)
         _chk(a); _chk(w, a.dtype); _chk(out)
         N, H, W, Cin = a.shape
         d = _lib.ConvDesc()
@@ -115,9 +139,10 @@ class CudaOps:
             assert residual.shape == out.shape
             d.residual = _p(residual)
         d.out, d.out_dtype, d.Cout = _p(out), _DT[out.dtype], out.shape[3]
-        assert w.shape[0] == d.Cout and w.shape[1] == ksize * ksize * Cin + (a2.shape[3] if a2 is not None else 0), \
-            f"packed weight {tuple(w.shape)} does not match conv {Cin}->{d.Cout} k{ksize}"
+        assert wshape[0] == d.Cout and wshape[1] == ksize * ksize * Cin + (a2.shape[3] if a2 is not None else 0), \
+            f"packed weight {wshape} does not match conv {Cin}->{d.Cout} k{ksize}"
         d.accumulate = int(accumulate)
+        d.w_tiled = int(tiled)
         if tune:
             d.block_n, d.split_k, d.stages = tune.get("block_n", 0), tune.get("split_k", 0), tune.get("stages", 0)
         ws, ws_bytes = self._workspace(self.lib.isb_conv2d_workspace(C.byref(d)))

@@ -11,7 +11,7 @@ from tests.conv_cases import CASES
 from tests.ref_ops import RefOps
 
 
-def run_case(ops, case, mode):
+def run_case(ops, case, mode, packed=True):
     name, N, H, W, Cin, Cout, k, Cin2, has_bias, has_res, acc, out_bf16, tune = case
     lo = torch.bfloat16 if mode == "bf16" else torch.float32
     g = torch.Generator().manual_seed(hash(name) % 1000)
@@ -27,7 +27,8 @@ def run_case(ops, case, mode):
     ref.conv(a, w, bias, k, out_ref, a2=a2, residual=res, accumulate=acc)
     d = ops.device
     out = out0.clone().to(d)
-    ops.conv(a.to(d), w.to(d), bias.to(d) if has_bias else None, k, out, a2=a2.to(d) if Cin2 else None,
+    w_dev = ops.pack_weight(w.to(d)) if packed else w.to(d)     # panel-tiled layout when the shape allows
+    ops.conv(a.to(d), w_dev, bias.to(d) if has_bias else None, k, out, a2=a2.to(d) if Cin2 else None,
              residual=res.to(d) if has_res else None, accumulate=acc, tune=tune)
     torch.cuda.synchronize()
     o = out.float().cpu()
@@ -47,6 +48,8 @@ if __name__ == "__main__":
         if mode == "fp32" and case[11]:
             continue
         err, mx, o, r = run_case(ops, case, mode)
+        err_u, _, _, _ = run_case(ops, case, mode, packed=False)
+        err = max(err, err_u)
         tol = 1e-2 if case[11] else (2e-3 if mode == "bf16" else 1e-5)
         print(f"[probe_conv {mode}] {case[0]:34s} rel_l2={err:.3e} max_abs={mx:.3e} {'OK' if err < tol else 'FAIL'}", flush=True)
         if err >= tol:

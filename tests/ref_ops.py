@@ -55,6 +55,9 @@ class RefOps:
         return dst
 
     # ---- conv ----
+    def pack_weight(self, w2d):
+        return w2d.contiguous()
+
     def conv(self, a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None):
         N, H, W, Cin = a.shape
         Cout = out.shape[3]

@@ -16,9 +16,10 @@ def ops_by_mode():
     return {m: CudaOps(torch.device("cuda", 0), m) for m in ("bf16", "fp32")}
 
 
+@pytest.mark.parametrize("packed", [True, False], ids=["panels", "rowmajor"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_conv_bf16_tcgen05(ops_by_mode, case):
-    err, mx, _, _ = run_case(ops_by_mode["bf16"], case, "bf16")
+def test_conv_bf16_tcgen05(ops_by_mode, case, packed):
+    err, mx, _, _ = run_case(ops_by_mode["bf16"], case, "bf16", packed=packed)
     # operands are identical bf16 values on both sides; only the accumulation order (and the bf16
     # output rounding when requested) differs
     assert err < (1e-2 if case[11] else 2e-3), f"rel_l2={err} max_abs={mx}"
