@@ -523,26 +523,22 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   p.chunks1 = d->a2 ? d->Cin2 / 64 : 0;
   p.k_iters = p.ntaps * p.chunks0 + p.chunks1;
   const int mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  // N tile / split-K / pipeline depth.  Goal: about one CTA per SM (or two when two fit), each with
-  // at least two k-iterations; small-M layers are weight-streaming bound, so they trade a narrower
-  // N tile for more CTAs pulling weights concurrently.
+  // N tile / split-K / pipeline depth, from the cold-weight sweep in profiles/r01_conv_tune_sweep_v1.txt:
+  //  * a launch costs ~6-8 us of fixed latency (prologue, first TMA, epilogue, cluster barriers), so the
+  //    aim is enough CTAs to overlap those phases — about two per SM — not "one wave";
+  //  * split-K (cluster of 2/4/8 CTAs per output tile, DSMEM fold) as long as every CTA keeps >= 3
+  //    k-iterations; 1x1 / linear layers (short K) prefer 64-wide N tiles, 3x3 layers 128-wide.
   const int sms = num_sms();
-  auto splits_for = [&](int tiles) {   // cluster split-K: 1, 2, 4 or 8 CTAs per output tile
+  auto splits_for = [&](int tiles) {
     int sp = 1;
-    while (sp < 8 && tiles * sp * 2 <= sms && sp * 2 <= p.k_iters / 2) sp *= 2;
+    while (sp < 8 && static_cast<long long>(tiles) * sp * 2 <= 2LL * sms && p.k_iters / (sp * 2) >= 3) sp *= 2;
     return sp;
   };
   int bn = d->block_n;
   if (bn == 0) {
     if (d->Cout < 128) bn = d->Cout;                                  // 32,64,96
     else if (d->Cout % 128 != 0 && d->Cout <= 256) bn = d->Cout;      // e.g. 192: one exact tile
-    else {
-      bn = 128;
-      const int t128 = mtiles * cdiv(d->Cout, 128), t64 = mtiles * cdiv(d->Cout, 64);
-      if (d->Cout % 64 == 0 && t128 < sms &&
-          static_cast<long long>(t64) * splits_for(t64) * 10 > static_cast<long long>(t128) * splits_for(t128) * 13)
-        bn = 64;
-    }
+    else bn = (d->ksize == 1 && d->Cout % 64 == 0) ? 64 : 128;
   }
   ISB_CHECK_ARG(bn >= 32 && bn <= 256 && bn % 32 == 0, "conv_tc: block_n=%d must be a multiple of 32 in [32,256]", bn);
   p.block_n = bn;

@@ -8,6 +8,7 @@ imported from here.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -51,6 +52,7 @@ class CudaOps:
         self.mode = mode
         self.lo = torch.bfloat16 if mode == "bf16" else torch.float32
         self.lib = _lib.init(self.device.index or 0)
+        self.tile_weights = os.environ.get("ISB_TILED_WEIGHTS", "0") == "1"
         self._ws = None
         self._gn_scratch = None
         self._gn_scratch_n = 0
@@ -111,7 +113,9 @@ class CudaOps:
         blocks and the K loop walks HBM sequentially (the row-major layout scatters each box over `bn`
         rows that are K*2 bytes apart)."""
         cout, k = w2d.shape
-        if self.mode == "bf16" and cout % 64 == 0 and k % 64 == 0:
+        # measured (profiles/r01_ablation.md): panels are NOT faster than row-major on B200 — the 128-byte
+        # rows of a box already spread over HBM channels — so the layout is opt-in (ISB_TILED_WEIGHTS=1)
+        if self.tile_weights and self.mode == "bf16" and cout % 64 == 0 and k % 64 == 0:
             t = w2d.reshape(cout // 64, 64, k // 64, 64).permute(0, 2, 1, 3).contiguous()
             return PackedWeight(t, cout, k, True)
         return PackedWeight(w2d.contiguous(), cout, k, False)
