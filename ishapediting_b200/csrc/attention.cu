@@ -101,32 +101,49 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, cons
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// stage a [64 rows x 32 k] operand tile into smem as bf16, rows = m (or n), k contiguous
+// A [64 rows x 32 k] operand tile travels global(fp32) -> registers -> smem(bf16, rows x k, k contiguous).
+// Two-phase so that the next tile's global loads are in flight while the tensor cores chew the current one.
+//   KMAJOR  (row*ld + k): 4 x float4 along k per thread, 8-byte smem stores.
+//   !KMAJOR (k*ld + row): thread owns one row and 16 consecutive k; 16 scalar loads, each coalesced across
+//                         the warp (consecutive rows), two conflict-free 16-byte smem stores.
 template <bool KMAJOR>
-__device__ __forceinline__ void tg_load_tile(const float* __restrict__ src, int ld, int row0, int k0,
-                                             __nv_bfloat16 (*sm)[TG_LD]) {
+__device__ __forceinline__ void tg_fetch(const float* __restrict__ src, int ld, int row0, int k0, float* r) {
   const int tid = threadIdx.x;
   if (KMAJOR) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * 128;
-      const int r = idx >> 3, kv = (idx & 7) * 4;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(row0 + r) * ld + k0 + kv));
-      uint2 u;
-      u.x = pack_bf16x2(v.x, v.y);
-      u.y = pack_bf16x2(v.z, v.w);
-      *reinterpret_cast<uint2*>(&sm[r][kv]) = u;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(row0 + (idx >> 3)) * ld + k0 + (idx & 7) * 4));
+      r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
     }
   } else {
+    const int row = tid & 63, kb = (tid >> 6) * 16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = __ldg(src + static_cast<size_t>(k0 + kb + j) * ld + row0 + row);
+  }
+}
+template <bool KMAJOR>
+__device__ __forceinline__ void tg_stash(const float* r, __nv_bfloat16 (*sm)[TG_LD]) {
+  const int tid = threadIdx.x;
+  if (KMAJOR) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * 128;
-      const int k = idx >> 4, rv = (idx & 15) * 4;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(k0 + k) * ld + row0 + rv));
-      sm[rv + 0][k] = __float2bfloat16_rn(v.x);
-      sm[rv + 1][k] = __float2bfloat16_rn(v.y);
-      sm[rv + 2][k] = __float2bfloat16_rn(v.z);
-      sm[rv + 3][k] = __float2bfloat16_rn(v.w);
+      uint2 u;
+      u.x = pack_bf16x2(r[4 * i], r[4 * i + 1]);
+      u.y = pack_bf16x2(r[4 * i + 2], r[4 * i + 3]);
+      *reinterpret_cast<uint2*>(&sm[idx >> 3][(idx & 7) * 4]) = u;
+    }
+  } else {
+    const int row = tid & 63, kb = (tid >> 6) * 16;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 u;
+      u.x = pack_bf16x2(r[8 * h], r[8 * h + 1]);
+      u.y = pack_bf16x2(r[8 * h + 2], r[8 * h + 3]);
+      u.z = pack_bf16x2(r[8 * h + 4], r[8 * h + 5]);
+      u.w = pack_bf16x2(r[8 * h + 6], r[8 * h + 7]);
+      *reinterpret_cast<uint4*>(&sm[row][kb + 8 * h]) = u;
     }
   }
 }
@@ -154,11 +171,18 @@ bgemm_mma_kernel(const BgemmParams p) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
 
+  float ra[16], rb[16];
+  tg_fetch<A_K>(A, p.lda, m0, 0, ra);
+  tg_fetch<B_K>(B, p.ldb, n0, 0, rb);
   for (int k0 = 0; k0 < p.K; k0 += TG_BK) {
+    __syncthreads();   // previous tile's fragment loads are done
+    tg_stash<A_K>(ra, As);
+    tg_stash<B_K>(rb, Bs);
     __syncthreads();
-    tg_load_tile<A_K>(A, p.lda, m0, k0, As);
-    tg_load_tile<B_K>(B, p.ldb, n0, k0, Bs);
-    __syncthreads();
+    if (k0 + TG_BK < p.K) {
+      tg_fetch<A_K>(A, p.lda, m0, k0 + TG_BK, ra);
+      tg_fetch<B_K>(B, p.ldb, n0, k0 + TG_BK, rb);
+    }
 #pragma unroll
     for (int kk = 0; kk < TG_BK; kk += 16) {
       uint32_t af[2][4], bf[4][2];
