@@ -124,23 +124,10 @@ __device__ __forceinline__ void gn_act8(const GnArgs& a, const float* x, float m
   }
 }
 
-__global__ void __launch_bounds__(256)
-gn_apply_kernel(const GnArgs a, const GnFwdOut o) {
-  pdl_trigger();
-  pdl_wait();
-  const int CV = a.C / 8;
-  const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;  // thread grid
-  const long long total = static_cast<long long>(a.N) * Ho * Wo * CV;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cv = static_cast<int>(idx % CV);
-  long long t = idx / CV;
-  const int w = static_cast<int>(t % Wo); t /= Wo;
-  const int h = static_cast<int>(t % Ho);
-  const int n = static_cast<int>(t / Ho);
-  const int c0 = cv * 8;
-  const int g = c0 / a.Cg;
-  const float mean = a.stats[(n * a.groups + g) * 2], rstd = a.stats[(n * a.groups + g) * 2 + 1];
+// one (output-grid pixel, 8-channel vector) of the apply pass
+__device__ __forceinline__ void gn_apply_one(const GnArgs& a, const GnFwdOut& o, int n, int h, int w, int c0,
+                                             float mean, float rstd) {
+  const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;
   float ga[8], be[8];
   gn_affine8(a, n, c0, ga, be);
   if (a.resample == 0) {
@@ -185,6 +172,68 @@ gn_apply_kernel(const GnArgs a, const GnFwdOut o) {
         store8(o.y, off, o.y_dtype, y);
         if (o.xres) store8(o.xres, off, ISB_F32, x);
       }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const GnArgs a, const GnFwdOut o) {
+  pdl_trigger();
+  pdl_wait();
+  const int CV = a.C / 8;
+  const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;  // thread grid
+  const long long total = static_cast<long long>(a.N) * Ho * Wo * CV;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = static_cast<int>(idx % CV);
+  long long t = idx / CV;
+  const int w = static_cast<int>(t % Wo); t /= Wo;
+  const int h = static_cast<int>(t % Ho);
+  const int n = static_cast<int>(t / Ho);
+  const int c0 = cv * 8;
+  const int g = c0 / a.Cg;
+  gn_apply_one(a, o, n, h, w, c0, a.stats[(n * a.groups + g) * 2], a.stats[(n * a.groups + g) * 2 + 1]);
+}
+
+// Small tensors: ONE launch, one CTA per (image, group): statistics pass, block reduction, apply pass
+// (the second read of the group's slice hits L1/L2).  Saves a launch and the global round trip.
+__global__ void __launch_bounds__(512)
+gn_fused_fwd_kernel(const GnArgs a, const GnFwdOut o) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ double sh0[16], sh1[16];
+  __shared__ float s_mean, s_rstd;
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int V = a.Cg / 8;
+  const int total = a.HW * V;
+  float s = 0.f, ss = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    float v[8];
+    gn_load_x8(a, n, i / V, g * a.Cg + (i % V) * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += v[j]; ss = fmaf(v[j], v[j], ss); }
+  }
+  double d0 = warp_sum_d(static_cast<double>(s)), d1 = warp_sum_d(static_cast<double>(ss));
+  if ((threadIdx.x & 31) == 0) { sh0[threadIdx.x >> 5] = d0; sh1[threadIdx.x >> 5] = d1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0, t1 = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { t0 += sh0[w]; t1 += sh1[w]; }
+    const double m = static_cast<double>(a.HW) * a.Cg;
+    const double mean = t0 / m;
+    double var = t1 / m - mean * mean;
+    if (var < 0) var = 0;
+    s_mean = static_cast<float>(mean);
+    s_rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+    a.stats[(n * a.groups + g) * 2 + 0] = s_mean;
+    a.stats[(n * a.groups + g) * 2 + 1] = s_rstd;
+  }
+  __syncthreads();
+  const float mean = s_mean, rstd = s_rstd;
+  const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;
+  const int total_o = Ho * Wo * V;
+  for (int i = threadIdx.x; i < total_o; i += blockDim.x) {
+    const int pix = i / V;
+    gn_apply_one(a, o, n, pix / Wo, pix % Wo, g * a.Cg + (i % V) * 8, mean, rstd);
   }
 }
 
@@ -265,24 +314,8 @@ gn_bwd_reduce_kernel(const GnArgs a, const GnBwdArgs b) {
   }
 }
 
-__global__ void __launch_bounds__(256)
-gn_bwd_apply_kernel(const GnArgs a, const GnBwdArgs b) {
-  pdl_trigger();
-  pdl_wait();
-  const int CV = a.C / 8;
-  const long long total = static_cast<long long>(a.N) * a.HW * CV;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cv = static_cast<int>(idx % CV);
-  long long t = idx / CV;
-  const int w = static_cast<int>(t % a.W); t /= a.W;
-  const int h = static_cast<int>(t % a.H);
-  const int n = static_cast<int>(t / a.H);
-  const int c0 = cv * 8;
-  const int g = c0 / a.Cg;
-  const int sg = n * a.groups + g;
-  const float mean = a.stats[sg * 2], rstd = a.stats[sg * 2 + 1];
-  const float m1 = a.bstats[sg * 2], m2 = a.bstats[sg * 2 + 1];
+__device__ __forceinline__ void gn_bwd_apply_one(const GnArgs& a, const GnBwdArgs& b, int n, int h, int w, int c0,
+                                                 float mean, float rstd, float m1, float m2) {
   float dzg[8], xhat[8], dx[8];
   gn_bwd_terms8(a, b, n, h, w, c0, mean, rstd, dzg, xhat);
 #pragma unroll
@@ -308,6 +341,64 @@ gn_bwd_apply_kernel(const GnArgs a, const GnBwdArgs b) {
   if (gx != nullptr) store8(gx, off, ISB_F32, dx);
   if (lo != nullptr) store8(lo, off, b.lo_dtype, dx);
 }
+
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const GnArgs a, const GnBwdArgs b) {
+  pdl_trigger();
+  pdl_wait();
+  const int CV = a.C / 8;
+  const long long total = static_cast<long long>(a.N) * a.HW * CV;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = static_cast<int>(idx % CV);
+  long long t = idx / CV;
+  const int w = static_cast<int>(t % a.W); t /= a.W;
+  const int h = static_cast<int>(t % a.H);
+  const int n = static_cast<int>(t / a.H);
+  const int c0 = cv * 8;
+  const int sg = n * a.groups + c0 / a.Cg;
+  gn_bwd_apply_one(a, b, n, h, w, c0, a.stats[sg * 2], a.stats[sg * 2 + 1], a.bstats[sg * 2], a.bstats[sg * 2 + 1]);
+}
+
+// single-launch backward for small tensors (see gn_fused_fwd_kernel)
+__global__ void __launch_bounds__(512)
+gn_fused_bwd_kernel(const GnArgs a, const GnBwdArgs b) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ double sh0[16], sh1[16];
+  __shared__ float s_m1, s_m2;
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int V = a.Cg / 8;
+  const int total = a.HW * V;
+  const float mean = a.stats[(n * a.groups + g) * 2], rstd = a.stats[(n * a.groups + g) * 2 + 1];
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pix = i / V;
+    float dzg[8], xhat[8];
+    gn_bwd_terms8(a, b, n, pix / a.W, pix % a.W, g * a.Cg + (i % V) * 8, mean, rstd, dzg, xhat);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 += dzg[j]; s2 = fmaf(dzg[j], xhat[j], s2); }
+  }
+  double d0 = warp_sum_d(static_cast<double>(s1)), d1 = warp_sum_d(static_cast<double>(s2));
+  if ((threadIdx.x & 31) == 0) { sh0[threadIdx.x >> 5] = d0; sh1[threadIdx.x >> 5] = d1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0, t1 = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { t0 += sh0[w]; t1 += sh1[w]; }
+    const double m = static_cast<double>(a.HW) * a.Cg;
+    s_m1 = static_cast<float>(t0 / m);
+    s_m2 = static_cast<float>(t1 / m);
+  }
+  __syncthreads();
+  const float m1 = s_m1, m2 = s_m2;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pix = i / V;
+    gn_bwd_apply_one(a, b, n, pix / a.W, pix % a.W, g * a.Cg + (i % V) * 8, mean, rstd, m1, m2);
+  }
+}
+
+// one CTA per (image, group) is enough when a group's slice is small (everything below 128x128 here)
+static bool gn_use_fused(const GnArgs& a) { return static_cast<long long>(a.HW) * a.Cg <= 65536; }
 
 static int gn_fill_args(const isb_gn_desc* d, void* scratch, GnArgs* a) {
   ISB_CHECK_ARG(d->x1 != nullptr && d->C1 > 0, "groupnorm: x1 missing");
@@ -366,9 +457,14 @@ int isb_gn_forward(const isb_gn_desc* d, void* scratch, isb_stream_t stream) {
   if (rc) return rc;
   ISB_CHECK_ARG(d->y != nullptr, "isb_gn_forward: y missing");
   cudaStream_t st = isb::as_stream(stream);
+  isb::GnFwdOut o{d->y, d->y_dtype, d->raw, d->raw_dtype, d->xres};
+  if (isb::gn_use_fused(a)) {
+    ISB_CUDA(isb::launch(isb::gn_fused_fwd_kernel, dim3(a.groups, a.N), 512, 0, st, a, o));
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+  }
   ISB_CUDA(isb::launch(isb::gn_stats_kernel, dim3(a.splits, a.groups, a.N), 256, 0, st, a));
   ISB_LAUNCH_CHECK();
-  isb::GnFwdOut o{d->y, d->y_dtype, d->raw, d->raw_dtype, d->xres};
   const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;
   const long long total = static_cast<long long>(a.N) * Ho * Wo * (a.C / 8);
   ISB_CUDA(isb::launch(isb::gn_apply_kernel, isb::cdiv(total, 256), 256, 0, st, a, o));
@@ -386,6 +482,11 @@ int isb_gn_backward(const isb_gn_bwd_desc* d, void* scratch, isb_stream_t stream
   isb::GnBwdArgs b{d->dy, d->gres, d->gres_at_input, d->gx1, d->acc1, d->gx1_lo,
                    d->gx2, d->acc2, d->gx2_lo, d->lo_dtype};
   cudaStream_t st = isb::as_stream(stream);
+  if (isb::gn_use_fused(a)) {
+    ISB_CUDA(isb::launch(isb::gn_fused_bwd_kernel, dim3(a.groups, a.N), 512, 0, st, a, b));
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+  }
   ISB_CUDA(isb::launch(isb::gn_bwd_reduce_kernel, dim3(a.splits, a.groups, a.N), 256, 0, st, a, b));
   ISB_LAUNCH_CHECK();
   const long long total = static_cast<long long>(a.N) * a.HW * (a.C / 8);

@@ -47,7 +47,9 @@ GN_CASES = [
     (1, 16, 16, 256, 0, False, True, 1, False),      # down
     (1, 8, 8, 256, 0, False, True, 2, False),        # up
     (1, 32, 32, 512, 0, False, False, 0, False),     # attention norm (no silu)
-    (1, 64, 64, 256, 0, True, True, 0, False),       # multi-split statistics
+    (1, 64, 64, 256, 0, True, True, 0, False),       # largest slice still on the single-launch path
+    (1, 128, 128, 256, 0, True, True, 0, False),     # two-kernel path, multi-split statistics
+    (1, 128, 128, 256, 0, False, True, 1, False),    # two-kernel path + avg-pool
 ]
 
 
