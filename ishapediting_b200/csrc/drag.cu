@@ -8,8 +8,9 @@
 //     handle, each with multiplicity (2r+1): the host passes the distinct points + weights;
 //   * kernel 1 samples origin@patch and edit@shift bilinearly (align_corners=True, zeros
 //     padding) and stores the per-point loss derivative g;
-//   * kernel 2 is a GATHER over feature pixels (no atomics -> bit-reproducible): each pixel
-//     walks the points of the handles whose bounding box covers it, adds the mask-regulariser
+//   * kernel 2 is a GATHER over (plane, pixel) (no atomics -> bit-reproducible): each CTA compacts,
+//     in point order, the samples whose footprint covers its pixel (bounding boxes prune whole
+//     handles), then one thread per aligned channel accumulates them, adds the mask-regulariser
 //     term and writes dLoss/dfeat straight into the NHWC feature gradient;
 //   * kernel 3 folds the loss partials in fixed order.
 #include "common.cuh"
@@ -101,58 +102,113 @@ drag_sample_kernel(const DragArgs a) {
   }
 }
 
-// one thread per (pixel, feature channel)
-__global__ void __launch_bounds__(256)
+// one CTA per (plane, pixel), one thread per aligned channel.  The warps first build — in point order, so
+// the summation order is fixed — the short list of sample points whose bilinear footprint covers this
+// pixel (bounding boxes prune whole handles), then every channel thread walks that list.
+constexpr int DG_THREADS = 192;
+constexpr int DG_MAXLIST = 1024;
+
+__global__ void __launch_bounds__(DG_THREADS)
 drag_gather_kernel(const DragArgs a) {
   pdl_trigger();
   pdl_wait();
+  __shared__ int s_j[DG_MAXLIST];
+  __shared__ float s_w[DG_MAXLIST];
+  __shared__ int s_cnt[DG_THREADS / 32 + 1];
+  __shared__ float red[DG_THREADS / 32];
   const int S = a.S;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(S) * S * a.Cf;
-  float msq = 0.f;
-  if (idx < total) {
-    const int c = static_cast<int>(idx % a.Cf);
-    const int pix = static_cast<int>(idx / a.Cf);
-    const int x = pix % S, y = pix / S;
-    const int m = a.inv_map[c];
-    float d = 0.f;
-    if (m >= 0) {
-      const int pl = m / a.Ca, ch = m - pl * a.Ca;
-      float acc = 0.f;
-      for (int grp = 0; grp < a.ngroups; ++grp) {
-        const int4 bb = __ldg(reinterpret_cast<const int4*>(a.bbox) + pl * a.ngroups + grp);
-        if (x < bb.x || x > bb.y + 1 || y < bb.z || y > bb.w + 1) continue;
-        const int jbeg = grp * a.group_size;
-        for (int jj = 0; jj < a.group_size; ++jj) {
-          const size_t pj = static_cast<size_t>(pl) * a.npts + jbeg + jj;
-          const float4 info = reinterpret_cast<const float4*>(a.pt_info)[pj];
-          const int x0 = static_cast<int>(info.x), y0 = static_cast<int>(info.y);
-          const int ddx = x - x0, ddy = y - y0;
-          if (ddx < 0 || ddx > 1 || ddy < 0 || ddy > 1) continue;
-          const float w = (ddx ? info.z : 1.0f - info.z) * (ddy ? info.w : 1.0f - info.w);
-          acc = fmaf(w, a.g[pj * a.Ca + ch], acc);
-        }
-      }
-      d = -a.inv_count * acc;
-      if (a.cof > 0.f && a.mask[(static_cast<size_t>(pl) * S + y) * S + x]) {
-        const float e = a.feat[idx];
-        const float o = __ldg(a.origin + ((static_cast<size_t>(pl) * S + y) * S + x) * a.Ca + ch);
-        const float df = e - o;
-        const float norm = 1.0f / (static_cast<float>(a.Ca) * static_cast<float>(a.mask_count));
-        if (a.loss_type == 0) { d -= a.cof * 2.0f * df * norm; msq = df * df; }
-        else { d -= a.cof * static_cast<float>((df > 0.f) - (df < 0.f)) * norm; msq = fabsf(df); }
+  const int pix = blockIdx.x, pl = blockIdx.y;
+  const int x = pix % S, y = pix / S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = DG_THREADS / 32;
+
+  // pass 1: count per warp (each warp owns a contiguous segment of the point list)
+  const int seg = (a.npts + nwarps - 1) / nwarps;
+  const int jbeg = warp * seg, jend = min(a.npts, jbeg + seg);
+  int my_count = 0;
+  for (int j0 = jbeg; j0 < jend; j0 += 32) {
+    const int j = j0 + lane;
+    bool hit = false;
+    if (j < jend) {
+      const int4 bb = __ldg(reinterpret_cast<const int4*>(a.bbox) + pl * a.ngroups + j / a.group_size);
+      if (!(x < bb.x || x > bb.y + 1 || y < bb.z || y > bb.w + 1)) {
+        const float4 info = reinterpret_cast<const float4*>(a.pt_info)[static_cast<size_t>(pl) * a.npts + j];
+        const int ddx = x - static_cast<int>(info.x), ddy = y - static_cast<int>(info.y);
+        hit = ddx >= 0 && ddx <= 1 && ddy >= 0 && ddy <= 1;
       }
     }
-    a.d_feat[idx] = d;
+    my_count += __popc(__ballot_sync(0xffffffffu, hit));
   }
-  __shared__ float red[8];
+  if (lane == 0) s_cnt[warp] = my_count;
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int w = 0; w < nwarps; ++w) {
+    if (w < warp) base += s_cnt[w];
+    total += s_cnt[w];
+  }
+  // pass 2: ordered compaction into the shared list
+  if (total > 0 && total <= DG_MAXLIST) {
+    int pos = base;
+    for (int j0 = jbeg; j0 < jend; j0 += 32) {
+      const int j = j0 + lane;
+      bool hit = false;
+      float w = 0.f;
+      if (j < jend) {
+        const int4 bb = __ldg(reinterpret_cast<const int4*>(a.bbox) + pl * a.ngroups + j / a.group_size);
+        if (!(x < bb.x || x > bb.y + 1 || y < bb.z || y > bb.w + 1)) {
+          const float4 info = reinterpret_cast<const float4*>(a.pt_info)[static_cast<size_t>(pl) * a.npts + j];
+          const int ddx = x - static_cast<int>(info.x), ddy = y - static_cast<int>(info.y);
+          hit = ddx >= 0 && ddx <= 1 && ddy >= 0 && ddy <= 1;
+          if (hit) w = (ddx ? info.z : 1.0f - info.z) * (ddy ? info.w : 1.0f - info.w);
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int k = pos + __popc(m & ((1u << lane) - 1u));
+        s_j[k] = j;
+        s_w[k] = w;
+      }
+      pos += __popc(m);
+    }
+  }
+  __syncthreads();
+
+  float msq = 0.f;
+  const bool masked = a.cof > 0.f && a.mask[(static_cast<size_t>(pl) * S + y) * S + x];
+  const float norm = masked ? 1.0f / (static_cast<float>(a.Ca) * static_cast<float>(a.mask_count)) : 0.f;
+  for (int ch = threadIdx.x; ch < a.Ca; ch += DG_THREADS) {
+    float acc = 0.f;
+    if (total <= DG_MAXLIST) {
+      for (int k = 0; k < total; ++k)
+        acc = fmaf(s_w[k], a.g[(static_cast<size_t>(pl) * a.npts + s_j[k]) * a.Ca + ch], acc);
+    } else {   // pathological overlap: walk the whole list (same order)
+      for (int j = 0; j < a.npts; ++j) {
+        const float4 info = reinterpret_cast<const float4*>(a.pt_info)[static_cast<size_t>(pl) * a.npts + j];
+        const int ddx = x - static_cast<int>(info.x), ddy = y - static_cast<int>(info.y);
+        if (ddx < 0 || ddx > 1 || ddy < 0 || ddy > 1) continue;
+        const float w = (ddx ? info.z : 1.0f - info.z) * (ddy ? info.w : 1.0f - info.w);
+        acc = fmaf(w, a.g[(static_cast<size_t>(pl) * a.npts + j) * a.Ca + ch], acc);
+      }
+    }
+    float d = -a.inv_count * acc;
+    const int src_c = a.chan_map[pl * a.Ca + ch];
+    const size_t fidx = static_cast<size_t>(pix) * a.Cf + src_c;
+    if (masked) {
+      const float df = a.feat[fidx] - __ldg(a.origin + ((static_cast<size_t>(pl) * S + y) * S + x) * a.Ca + ch);
+      if (a.loss_type == 0) { d -= a.cof * 2.0f * df * norm; msq += df * df; }
+      else { d -= a.cof * static_cast<float>((df > 0.f) - (df < 0.f)) * norm; msq += fabsf(df); }
+    }
+    a.d_feat[fidx] = d;
+  }
+  if (pl == 0)   // channels resize_feat_align drops get a zero gradient
+    for (int c = threadIdx.x; c < a.Cf; c += DG_THREADS)
+      if (a.inv_map[c] < 0) a.d_feat[static_cast<size_t>(pix) * a.Cf + c] = 0.f;
   msq = warp_sum(msq);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = msq;
+  if (lane == 0) red[warp] = msq;
   __syncthreads();
   if (threadIdx.x == 0) {
-    double s = 0;
-    for (int w = 0; w < 8; ++w) s += red[w];
-    a.partial[static_cast<size_t>(3) * a.npts + blockIdx.x] = s;
+    double sum = 0;
+    for (int w = 0; w < nwarps; ++w) sum += red[w];
+    a.partial[static_cast<size_t>(3) * a.npts + static_cast<size_t>(pl) * S * S + pix] = sum;
   }
 }
 
@@ -198,8 +254,8 @@ resize_feat_align_kernel(const float* __restrict__ feat, int S, int Cf, const in
 extern "C" {
 
 size_t isb_drag_partial_len(int S, int Cf, int npts) {
-  const long long total = static_cast<long long>(S) * S * Cf;
-  return static_cast<size_t>(3) * npts + static_cast<size_t>((total + 255) / 256);
+  (void)Cf;
+  return static_cast<size_t>(3) * npts + static_cast<size_t>(3) * S * S;
 }
 
 int isb_drag_loss_grad(const isb_drag_desc* d, isb_stream_t stream) {
@@ -209,8 +265,7 @@ int isb_drag_loss_grad(const isb_drag_desc* d, isb_stream_t stream) {
   ISB_CHECK_ARG(d->S > 1 && d->Cf > 0 && d->Ca > 0 && d->npts > 0, "isb_drag_loss_grad: bad shape");
   ISB_CHECK_ARG(d->group_size > 0 && d->npts % d->group_size == 0, "isb_drag_loss_grad: npts must be a multiple of group_size");
   ISB_CHECK_ARG(d->cof <= 0.f || (d->mask != nullptr && d->mask_count > 0), "isb_drag_loss_grad: mask required when cof > 0");
-  const long long total = static_cast<long long>(d->S) * d->S * d->Cf;
-  const int gblocks = isb::cdiv(total, 256);
+  const int gblocks = 3 * d->S * d->S;
   ISB_CHECK_ARG(static_cast<size_t>(d->partial_len) >= isb_drag_partial_len(d->S, d->Cf, d->npts), "isb_drag_loss_grad: partial buffer too small");
   isb::DragArgs a{d->feat, d->S, d->Cf, d->origin, d->Ca, d->chan_map, d->inv_map,
                   d->patch_xy, d->shift_xy, d->weight, d->npts, d->group_size, d->npts / d->group_size,
@@ -219,7 +274,7 @@ int isb_drag_loss_grad(const isb_drag_desc* d, isb_stream_t stream) {
   cudaStream_t st = isb::as_stream(stream);
   ISB_CUDA(isb::launch(isb::drag_sample_kernel, dim3(d->npts, 3), 192, 0, st, a));
   ISB_LAUNCH_CHECK();
-  ISB_CUDA(isb::launch(isb::drag_gather_kernel, gblocks, 256, 0, st, a));
+  ISB_CUDA(isb::launch(isb::drag_gather_kernel, dim3(d->S * d->S, 3), isb::DG_THREADS, 0, st, a));
   ISB_LAUNCH_CHECK();
   ISB_CUDA(isb::launch(isb::drag_loss_kernel, 1, 256, 0, st, a));
   ISB_LAUNCH_CHECK();

@@ -397,8 +397,9 @@ gn_fused_bwd_kernel(const GnArgs a, const GnBwdArgs b) {
   }
 }
 
-// one CTA per (image, group) is enough when a group's slice is small (everything below 128x128 here)
-static bool gn_use_fused(const GnArgs& a) { return static_cast<long long>(a.HW) * a.Cg <= 65536; }
+// one CTA per (image, group) only pays off for tiny slices (8x8, 16x16): measured, larger slices are
+// faster with the two wide kernels (32 CTAs cannot pull enough bandwidth)
+static bool gn_use_fused(const GnArgs& a) { return static_cast<long long>(a.HW) * a.Cg <= 8192; }
 
 static int gn_fill_args(const isb_gn_desc* d, void* scratch, GnArgs* a) {
   ISB_CHECK_ARG(d->x1 != nullptr && d->C1 > 0, "groupnorm: x1 missing");
