@@ -126,6 +126,39 @@ def cpu_reference_steps(n_steps, n_warm, budget_s=150.0):
                        f"input-gradient only) after {n_warm} warm-up")
 
 
+def torch_eager_gpu_steps(dev, n_steps=3):
+    """Informational comparator: the same oracle restatement (stock PyTorch ops + autograd, fp32, TF32 off)
+    executed on the B200 — i.e. what the reference's own code path costs on this GPU (the
+    reference has no Blackwell kernel; torch eager is the practical comparator)."""
+    import torch
+    from oracle import nfd_oracle as O
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.NFD_CFG
+    sd = {k: v.to(dev) for k, v in O.synth_state_dict(cfg).items()}
+    sched = O.Schedule(cfg["diffusion_steps"], cfg["timestep_respacing"])
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 96, 128, 128, generator=g).to(dev)
+    noise = torch.randn(1, 96, 128, 128, generator=g).to(dev)
+    origin = torch.randn(3, 170, 64, 64, generator=g).to(dev)
+    src, tgt = _problem(4)
+    pg, sg, masks = O.drag_setup(src, tgt, 12, 2.0 / 256, 64)
+    pg, sg = pg.to(dev), sg.to(dev)
+    ts = []
+    for k in range(n_steps + 1):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        out = O.guided_step(sd, cfg, sched, x, W_TIME - 1 - k, origin, noise, pg, sg, masks, scale=600.0, cof=0.2)
+        x = out["img"]
+        torch.cuda.synchronize()
+        if k > 0:
+            ts.append(time.time() - t0)
+    ms = 1e3 * sum(ts) / len(ts)
+    return {"value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms,
+            "what": "oracle restatement (stock torch ops + autograd, fp32, TF32 off) run eagerly on the same B200"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -285,6 +318,10 @@ def run_ours(args):
             "roofline": roof,
         }
         if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["torch_eager_b200"] = torch_eager_gpu_steps(dev)
+            except Exception as e:  # noqa: BLE001 - informational only
+                line["torch_eager_b200"] = {"error": repr(e)[:200]}
             r = cpu_reference_steps(2, 1, budget_s=60.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}

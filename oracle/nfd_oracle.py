@@ -167,7 +167,7 @@ def synth_state_dict(cfg, seed=1234, branch_gain=0.5):
 def timestep_embedding(t, dim, max_period=10000):
     """nn.py:102-120."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -285,7 +285,7 @@ def _f(a, i):
 def p_sample_guidance(sd, cfg, sched, x, i, noise, feat_layer=8, clip_denoised=True):
     """p_mean_variance + p_sample_guidance for EPSILON / LEARNED_RANGE
     (gaussian_diffusion.py:232-331, 446-510).  `i` is the respaced step index."""
-    t_orig = torch.full((x.shape[0],), sched.timestep_map[i], dtype=torch.int64)   # respace.py:122-124
+    t_orig = torch.full((x.shape[0],), sched.timestep_map[i], dtype=torch.int64, device=x.device)   # respace.py:122-124
     model_output, inter = unet_forward(sd, cfg, x, t_orig, feat_layer)
     C = x.shape[1]
     eps, v = torch.split(model_output, C, dim=1)
@@ -353,8 +353,8 @@ def drag_loss(edit_feature, origin_feature, patch_grid, shift_grid, masks, cof=0
     patch = F.grid_sample(origin_feature, patch_grid, mode="bilinear", padding_mode="zeros", align_corners=True)
     shift = F.grid_sample(edit_feature, shift_grid, mode="bilinear", padding_mode="zeros", align_corners=True)
     C = origin_feature.shape[1]
-    m = torch.from_numpy(masks)
-    cnt = int(m.sum())
+    m = torch.from_numpy(masks).to(edit_feature.device)
+    cnt = int(masks.sum())
     diff = (edit_feature - origin_feature) * m[:, None].float()
     if loss_type == "l1":
         mask_loss = diff.abs().sum() / (C * cnt) if cof > 0 else 0.0
