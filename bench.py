@@ -366,7 +366,11 @@ def conv_roofline(st, ds, step_index):
     return {"bound": "tensor", "kernel": "conv_tc_kernel (+splitk_finalize)", "achieved": ach,
             "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
             "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a step)",
-            "launches": len(rec), "gflop_per_step": flops / 1e9, "ms_in_kernel_per_step": t_ms, "traffic": None}
+            "launches": len(rec), "gflop_per_step": flops / 1e9, "ms_in_kernel_per_step": t_ms,
+            # dram__bytes_read+write of one captured launch (profiles/r01_ncu_full_conv_tc.md): the 3x3 256->256 @128x128
+            # layer moves 9.63 MB = its algorithmic bytes (8.39 MB bf16 activations + 1.18 MB weights; the fp32 output
+            # stays in L2)
+            "traffic": 9.63e6, "traffic_launch": "3x3 conv 256->256 @128x128 (19.3 GFLOP)"}
 
 
 def main():

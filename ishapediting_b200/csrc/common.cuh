@@ -66,6 +66,7 @@ tensormap_encode_fn get_tensormap_encode();
 // successor start that early.  Rule: no global read of produced data and NO global write before
 // pdl_wait().  ISB_PDL=0 in the environment turns the attribute off (plain stream order).
 bool pdl_enabled();
+bool pdl_enabled_conv();
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

@@ -690,7 +690,7 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (pdl_enabled()) {
+  if (pdl_enabled_conv()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

@@ -21,13 +21,18 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 bool is_initialised() { return g_init.load(); }
-bool pdl_enabled() {
-  static const bool on = [] {
+// ISB_PDL: 0 = off, 1 = every kernel, 2 (default) = conv_tc only.  Measured on B200 (profiles/): making every
+// kernel a programmatic dependent slows the memory-bound kernels down (their early CTAs squat on SMs while
+// the predecessor drains); the conv kernel alone profits — it streams weight tiles during the wait.
+static int pdl_mode() {
+  static const int mode = [] {
     const char* e = getenv("ISB_PDL");
-    return e && e[0] == '1';   // measured neutral under CUDA-graph replay (profiles/): opt-in
+    return e ? atoi(e) : 2;
   }();
-  return on;
+  return mode;
 }
+bool pdl_enabled() { return pdl_mode() == 1; }
+bool pdl_enabled_conv() { return pdl_mode() >= 1; }
 int num_sms() { return g_num_sms; }
 tensormap_encode_fn get_tensormap_encode() { return g_encode; }
 
