@@ -40,6 +40,10 @@ class PackedWeight:
     def __init__(self, data, cout, k, tiled):
         self.data, self.cout, self.k, self.tiled = data, cout, k, tiled
 
+    @property
+    def shape(self):
+        return (self.cout, self.k)
+
 
 class CudaOps:
     name = "cuda"
