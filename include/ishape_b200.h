@@ -236,6 +236,8 @@ typedef struct isb_drag_desc {
   float inv_count; float cof; int loss_type;
   float* g; float* pt_info; double* partial; int partial_len;
   float* loss; float* d_feat;
+  const float* dyn_scalars;  /* optional DEVICE [2] = {inv_count, 1/(Ca*mask_count)}: overrides the two by-value
+                                scalars so that one captured CUDA graph serves edits with different handles */
 } isb_drag_desc;
 size_t isb_drag_partial_len(int S, int Cf, int npts);
 int isb_drag_loss_grad(const isb_drag_desc* d, isb_stream_t stream);

@@ -83,7 +83,7 @@ class DragDesc(C.Structure):
         ("mask", c_void_p), ("mask_count", c_int),
         ("inv_count", c_float), ("cof", c_float), ("loss_type", c_int),
         ("g", c_void_p), ("pt_info", c_void_p), ("partial", c_void_p), ("partial_len", c_int),
-        ("loss", c_void_p), ("d_feat", c_void_p),
+        ("loss", c_void_p), ("d_feat", c_void_p), ("dyn_scalars", c_void_p),
     ]
 
 

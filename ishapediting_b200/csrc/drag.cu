@@ -28,6 +28,7 @@ struct DragArgs {
   float inv_count; float cof; int loss_type;
   float* g; float* pt_info; double* partial; int n_gather_blocks;
   float* loss; float* d_feat;
+  const float* dyn;   // optional device [2]: inv_count, 1/(Ca*mask_count) — overrides the by-value scalars
 };
 
 struct Bilin {
@@ -174,7 +175,8 @@ drag_gather_kernel(const DragArgs a) {
 
   float msq = 0.f;
   const bool masked = a.cof > 0.f && a.mask[(static_cast<size_t>(pl) * S + y) * S + x];
-  const float norm = masked ? 1.0f / (static_cast<float>(a.Ca) * static_cast<float>(a.mask_count)) : 0.f;
+  const float inv_count = a.dyn ? a.dyn[0] : a.inv_count;
+  const float norm = !masked ? 0.f : (a.dyn ? a.dyn[1] : 1.0f / (static_cast<float>(a.Ca) * static_cast<float>(a.mask_count)));
   for (int ch = threadIdx.x; ch < a.Ca; ch += DG_THREADS) {
     float acc = 0.f;
     if (total <= DG_MAXLIST) {
@@ -189,7 +191,7 @@ drag_gather_kernel(const DragArgs a) {
         acc = fmaf(w, a.g[(static_cast<size_t>(pl) * a.npts + j) * a.Ca + ch], acc);
       }
     }
-    float d = -a.inv_count * acc;
+    float d = -inv_count * acc;
     const int src_c = a.chan_map[pl * a.Ca + ch];
     const size_t fidx = static_cast<size_t>(pix) * a.Cf + src_c;
     if (masked) {
@@ -228,8 +230,10 @@ drag_loss_kernel(const DragArgs a) {
   if (threadIdx.x == 0) {
     double mo = 0, ma = 0;
     for (int w = 0; w < 8; ++w) { mo += red[0][w]; ma += red[1][w]; }
-    double loss = -mo * static_cast<double>(a.inv_count);
-    if (a.cof > 0.f && a.mask_count > 0) loss -= static_cast<double>(a.cof) * ma / (static_cast<double>(a.Ca) * a.mask_count);
+    const double inv_count = a.dyn ? a.dyn[0] : a.inv_count;
+    const double mnorm = a.dyn ? a.dyn[1] : (a.mask_count > 0 ? 1.0 / (static_cast<double>(a.Ca) * a.mask_count) : 0.0);
+    double loss = -mo * inv_count;
+    if (a.cof > 0.f) loss -= static_cast<double>(a.cof) * ma * mnorm;
     *a.loss = static_cast<float>(loss);
   }
 }
@@ -264,13 +268,13 @@ int isb_drag_loss_grad(const isb_drag_desc* d, isb_stream_t stream) {
                 "isb_drag_loss_grad: null pointer");
   ISB_CHECK_ARG(d->S > 1 && d->Cf > 0 && d->Ca > 0 && d->npts > 0, "isb_drag_loss_grad: bad shape");
   ISB_CHECK_ARG(d->group_size > 0 && d->npts % d->group_size == 0, "isb_drag_loss_grad: npts must be a multiple of group_size");
-  ISB_CHECK_ARG(d->cof <= 0.f || (d->mask != nullptr && d->mask_count > 0), "isb_drag_loss_grad: mask required when cof > 0");
+  ISB_CHECK_ARG(d->cof <= 0.f || (d->mask != nullptr && (d->mask_count > 0 || d->dyn_scalars != nullptr)), "isb_drag_loss_grad: mask required when cof > 0");
   const int gblocks = 3 * d->S * d->S;
   ISB_CHECK_ARG(static_cast<size_t>(d->partial_len) >= isb_drag_partial_len(d->S, d->Cf, d->npts), "isb_drag_loss_grad: partial buffer too small");
   isb::DragArgs a{d->feat, d->S, d->Cf, d->origin, d->Ca, d->chan_map, d->inv_map,
                   d->patch_xy, d->shift_xy, d->weight, d->npts, d->group_size, d->npts / d->group_size,
                   d->bbox, d->mask, d->mask_count, d->inv_count, d->cof, d->loss_type,
-                  d->g, d->pt_info, d->partial, gblocks, d->loss, d->d_feat};
+                  d->g, d->pt_info, d->partial, gblocks, d->loss, d->d_feat, d->dyn_scalars};
   cudaStream_t st = isb::as_stream(stream);
   ISB_CUDA(isb::launch(isb::drag_sample_kernel, dim3(d->npts, 3), 192, 0, st, a));
   ISB_LAUNCH_CHECK();

@@ -182,6 +182,7 @@ class GuidedStepper:
         ops = self.ops = self.plan.ops
         dev = ops.device
         self.geo = geometry.to(dev)
+        self.dyn = th.tensor([geometry.inv_count, 1.0 / (max(geometry.mask_count, 1))], dtype=th.float32, device=dev)
         self.feat_layer, self.cof, self.scale, self.clip = feat_layer, float(cof), float(scale), clip_denoised
         self.loss_type = 1 if loss_type == "l1" else 0
         inter = self.plan.block_out[feat_layer]
@@ -206,16 +207,35 @@ class GuidedStepper:
         self.partial = ops.zeros((ops.drag_partial_len(S, Cf, npts),), th.float64)
         self.loss = ops.zeros((1,))
         self.plan.ensure_grad(inter)
+        self.dyn[1] /= Ca
         self.use_graph = use_graph and dev.type == "cuda"
         self._graph = None
         self._warm = 0
+
+    def compatible(self, geometry, cof, loss_type):
+        """True if a new edit (other handles/targets, other scale) can reuse this stepper and its captured graph:
+        same number of sample points and the by-value kernel scalars (cof, loss type) unchanged."""
+        return (geometry.npts == self.geo.npts and geometry.group_size == self.geo.group_size
+                and float(cof) == self.cof and (1 if loss_type == "l1" else 0) == self.loss_type)
+
+    def retarget(self, geometry, scale):
+        """Load a new edit's geometry into the static device buffers (no re-capture)."""
+        g = geometry
+        for k in ("patch_xy", "shift_xy", "weight", "bbox", "mask"):
+            getattr(self.geo, k).copy_(getattr(g, k))
+        self.geo.mask_count, self.geo.inv_count = g.mask_count, g.inv_count
+        self.dyn.copy_(th.tensor([g.inv_count, 1.0 / (max(g.mask_count, 1) * self.Ca)], dtype=th.float32))
+        if float(scale) != self.scale:
+            self.scale = float(scale)
+            self.coef_table = self.diffusion.coef_table(self.ops.device, guide_scale=self.scale)
 
     def _body(self):
         plan, ops, geo = self.plan, self.ops, self.geo
         inter = plan.forward(self.img, plan.t_dev, self.feat_layer)
         ops.drag_loss_grad(inter.val, self.origin, self.chan_map, self.inv_map, geo.patch_xy, geo.shift_xy,
                            geo.weight, geo.group_size, geo.bbox, geo.mask, geo.mask_count, geo.inv_count,
-                           self.cof, self.loss_type, self.g, self.pt_info, self.partial, self.loss, inter.grad)
+                           self.cof, self.loss_type, self.g, self.pt_info, self.partial, self.loss, inter.grad,
+                           dyn=self.dyn)
         plan.begin_backward()
         plan.seed_grad(inter)
         plan.backward(self.grad)
@@ -366,8 +386,12 @@ class DragStuff:
         assert self.sources.shape[0] == self.targets.shape[0]
         S, Ca = self.feature_guidance[0].shape[1], self.feature_guidance[0].shape[3]
         geo = DragGeometry(np.asarray(sources), np.asarray(targets), self.r1, self.voxel_size, S, Ca)
-        stepper = GuidedStepper(self.model, self.diffusion, geo, self.args.feat_layer, cof, self.args.loss_type, scale,
-                                clip_denoised=True, use_graph=self.use_graph)
+        stepper = getattr(self, "stepper", None)
+        if stepper is not None and stepper.model is self.model and stepper.compatible(geo, cof, self.args.loss_type):
+            stepper.retarget(geo, scale)          # same captured graph, new handles
+        else:
+            stepper = GuidedStepper(self.model, self.diffusion, geo, self.args.feat_layer, cof, self.args.loss_type,
+                                    scale, clip_denoised=True, use_graph=self.use_graph)
         stepper.img.copy_(self.w.detach())
         self.stepper = stepper
         stop_time = 0

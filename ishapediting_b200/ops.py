@@ -265,7 +265,7 @@ class CudaOps:
         return int(self.lib.isb_drag_partial_len(S, Cf, npts))
 
     def drag_loss_grad(self, feat, origin, chan_map, inv_map, patch_xy, shift_xy, weight, group_size, bbox, mask,
-                       mask_count, inv_count, cof, loss_type, g, pt_info, partial, loss, d_feat):
+                       mask_count, inv_count, cof, loss_type, g, pt_info, partial, loss, d_feat, dyn=None):
         d = _lib.DragDesc()
         _chk(feat, torch.float32); _chk(origin, torch.float32); _chk(d_feat, torch.float32)
         d.feat, d.S, d.Cf = _p(feat), feat.shape[1], feat.shape[3]
@@ -280,6 +280,7 @@ class CudaOps:
         d.g, d.pt_info = _p(_chk(g, torch.float32)), _p(_chk(pt_info, torch.float32))
         d.partial, d.partial_len = _p(_chk(partial, torch.float64)), partial.numel()
         d.loss, d.d_feat = _p(_chk(loss, torch.float32)), _p(d_feat)
+        d.dyn_scalars = _p(_chk(dyn, torch.float32)) if dyn is not None else None
         _lib.check(self.lib.isb_drag_loss_grad(C.byref(d), _stream()), "isb_drag_loss_grad")
 
     # ---- triplane decoder ---------------------------------------------------------------------

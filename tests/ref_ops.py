@@ -196,7 +196,9 @@ class RefOps:
         return 1
 
     def drag_loss_grad(self, feat, origin, chan_map, inv_map, patch_xy, shift_xy, weight, group_size, bbox, mask,
-                       mask_count, inv_count, cof, loss_type, g, pt_info, partial, loss, d_feat):
+                       mask_count, inv_count, cof, loss_type, g, pt_info, partial, loss, d_feat, dyn=None):
+        if dyn is not None:
+            inv_count = float(dyn[0])
         S, Cf, Ca = feat.shape[1], feat.shape[3], origin.shape[3]
         f = feat.detach().clone().requires_grad_(True)
         with torch.enable_grad():
@@ -214,7 +216,8 @@ class RefOps:
             if cof > 0:
                 m = mask.float()[:, None]
                 dm = (edit - orig) * m
-                ml = ((dm ** 2).sum() if loss_type == 0 else dm.abs().sum()) / (Ca * mask_count)
+                mnorm = float(dyn[1]) if dyn is not None else 1.0 / (Ca * mask_count)
+                ml = ((dm ** 2).sum() if loss_type == 0 else dm.abs().sum()) * mnorm
                 total = total - cof * ml
             (gf,) = torch.autograd.grad(total, f)
         loss.copy_(total.detach().reshape(1))
