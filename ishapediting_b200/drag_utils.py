@@ -176,7 +176,7 @@ class GuidedStepper:
     noise) are refreshed in static device buffers before each replay."""
 
     def __init__(self, model, diffusion, geometry: DragGeometry, feat_layer, cof, loss_type, scale,
-                 clip_denoised=True, use_graph=True):
+                 clip_denoised=True, use_graph=True, overlap_tail=True):
         self.model, self.diffusion = model, diffusion
         self.plan = model.plan(1, model.image_size, model.image_size, want_backward=True)
         ops = self.ops = self.plan.ops
@@ -209,6 +209,10 @@ class GuidedStepper:
         self.plan.ensure_grad(inter)
         self.dyn[1] /= Ca
         self.use_graph = use_graph and dev.type == "cuda"
+        self.overlap_tail = overlap_tail
+        if dev.type == "cuda":
+            self._side = th.cuda.Stream(device=dev)
+            self._ev_fork, self._ev_join = th.cuda.Event(), th.cuda.Event()
         self._graph = None
         self._warm = 0
 
@@ -231,7 +235,18 @@ class GuidedStepper:
 
     def _body(self):
         plan, ops, geo = self.plan, self.ops, self.geo
-        inter = plan.forward(self.img, plan.t_dev, self.feat_layer)
+        overlap = self.overlap_tail and ops.device.type == "cuda"
+        inter = plan.forward(self.img, plan.t_dev, self.feat_layer, upto_feat_only=overlap)
+        if overlap:
+            # The layers behind the intermediate feature (output_blocks[9..14] + out: 292 of the 635 forward
+            # GFLOP, all at 64^2/128^2) only feed the DDPM update; the backward pass that starts here is a chain
+            # of small, latency-bound kernels.  Run the two concurrently and join before the update.
+            main = th.cuda.current_stream()
+            self._ev_fork.record(main)
+            with th.cuda.stream(self._side):
+                self._side.wait_event(self._ev_fork)
+                plan.forward_tail()
+                self._ev_join.record(self._side)
         ops.drag_loss_grad(inter.val, self.origin, self.chan_map, self.inv_map, geo.patch_xy, geo.shift_xy,
                            geo.weight, geo.group_size, geo.bbox, geo.mask, geo.mask_count, geo.inv_count,
                            self.cof, self.loss_type, self.g, self.pt_info, self.partial, self.loss, inter.grad,
@@ -239,6 +254,8 @@ class GuidedStepper:
         plan.begin_backward()
         plan.seed_grad(inter)
         plan.backward(self.grad)
+        if overlap:
+            th.cuda.current_stream().wait_event(self._ev_join)
         ops.ddpm_step(self.img, plan.out_nhwc, self.coef, self.clip, noise=self.noise, grad=self.grad,
                       x_next=self.img_next, sample=self.sample, var=self.variance)
         self.img.copy_(self.img_next)

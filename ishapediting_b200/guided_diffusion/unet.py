@@ -385,13 +385,27 @@ class _Plan:
         ops.conv(self.x_lo, self.w_in, self.b_in, 3, self.h0.val)
         inter = self.block_out[feat_layer] if feat_layer >= 0 else None
         stop_after = inter if (upto_feat_only and inter is not None) else None
-        for layer in self.layers:
+        self._tail_from = len(self.layers)
+        for li, layer in enumerate(self.layers):
             layer.forward()
             if stop_after is not None and layer.out is stop_after:
+                self._tail_from = li + 1
                 return inter
+        self.forward_out_layer()
+        return inter
+
+    def forward_out_layer(self):
+        ops = self.ops
         ops.gn_forward(self.h_last.val, None, self.out_g, self.out_b, None, 0, True, 0, self.out_stats, self.out_a)
         ops.conv(self.out_a, self.w_out, self.b_out, 3, self.out_nhwc)
-        return inter
+
+    def forward_tail(self):
+        """The rest of the forward pass after `forward(..., upto_feat_only=True)`: the layers behind the
+        intermediate feature and the output layer.  They do not lie on the guidance-gradient path, so the
+        guided step runs them on a second stream, concurrently with the backward pass."""
+        for layer in self.layers[self._tail_from:]:
+            layer.forward()
+        self.forward_out_layer()
 
     # -- backward ---------------------------------------------------------------------------------
     def begin_backward(self):

@@ -58,8 +58,7 @@ class CudaOps:
         self.lib = _lib.init(self.device.index or 0)
         self.tile_weights = os.environ.get("ISB_TILED_WEIGHTS", "0") == "1"
         self._ws = None
-        self._gn_scratch = None
-        self._gn_scratch_n = 0
+        self._gn_scratch = {}
 
     # ---- memory -----------------------------------------------------------
     def empty(self, shape, dtype=torch.float32):
@@ -78,13 +77,17 @@ class CudaOps:
             self._ws = torch.zeros(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
         return self._ws, self._ws.numel()
 
-    def _scratch(self, N, groups=32):
+    def _scratch(self, N, groups=32, which="fwd"):
+        """GroupNorm reduction scratch (arrival counters + partials).  Forward and backward kernels get
+        separate buffers: the guided step runs the tail of the forward pass concurrently with the backward
+        pass on a second stream."""
         need = N * groups
-        if self._gn_scratch is None or self._gn_scratch_n < need:
+        cur = self._gn_scratch.get(which)
+        if cur is None or cur[1] < need:
             nbytes = self.lib.isb_gn_scratch_bytes(N, groups)
-            self._gn_scratch = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-            self._gn_scratch_n = need
-        return self._gn_scratch
+            cur = (torch.zeros(nbytes, dtype=torch.uint8, device=self.device), need)
+            self._gn_scratch[which] = cur
+        return cur[0]
 
     # ---- layout -------------------------------------------------------------
     def to_nhwc(self, x_nchw, out):
@@ -206,7 +209,8 @@ class CudaOps:
             assert lo_dtype is None or lo_dtype == gx2_lo.dtype
             b.gx2_lo, lo_dtype = _p(_chk(gx2_lo)), gx2_lo.dtype
         b.lo_dtype = _DT[lo_dtype] if lo_dtype is not None else F32
-        _lib.check(self.lib.isb_gn_backward(C.byref(b), _p(self._scratch(x1.shape[0])), _stream()), "isb_gn_backward")
+        _lib.check(self.lib.isb_gn_backward(C.byref(b), _p(self._scratch(x1.shape[0], which="bwd")), _stream()),
+                   "isb_gn_backward")
 
     # ---- attention ----------------------------------------------------------------
     def attention_forward(self, qkv, heads, probs, out):

@@ -47,6 +47,8 @@ def bench(ops, a, weights, bias, k, out, tune, tiled, reps=4):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--warm", action="store_true", help="one weight copy: weights stay L2-resident")
+    ap.add_argument("--auto-only", action="store_true")
     args = ap.parse_args()
     ops = CudaOps(torch.device("cuda", 0), "bf16")
     dev = ops.device
@@ -54,16 +56,23 @@ def main():
         K = k * k * Cin
         wbytes = Cout * K * 2
         ncopies = max(4, min(64, int(400e6 // wbytes)))           # ring > L2 (126 MB) when weights are big
+        if args.warm:
+            ncopies = 1
         a = torch.randn(1, H, H, Cin, device=dev).to(torch.bfloat16)
         out = torch.empty(1, H, H, Cout, device=dev)
         bias = torch.randn(Cout, device=dev)
         base = [torch.randn(Cout, K, device=dev).to(torch.bfloat16) for _ in range(ncopies)]
+        if args.warm:
+            base = base * 16
         flops = 2.0 * H * H * Cout * K
         rows = []
         bns = [64, 128, 256] if Cout % 256 == 0 else [64, 128]
         splits = [1, 2, 4, 8]
         stages = [3, 6] if args.quick else [3, 4, 6]
         t_auto, _ = bench(ops, a, base, bias, k, out, None, False)
+        if args.auto_only:
+            print(f"H={H:3d} k{k} {Cin:4d}->{Cout:4d}  auto {t_auto:7.1f} us  ({flops / t_auto / 1e6:6.1f} TF/s, weights {wbytes / t_auto / 1e3:6.0f} GB/s)", flush=True)
+            continue
         for bn, sp, stg in itertools.product(bns, splits, stages):
             t, err = bench(ops, a, base, bias, k, out, {"block_n": bn, "split_k": sp, "stages": stg}, False)
             if t is not None:
