@@ -175,39 +175,46 @@ class GuidedStepper:
     sequence is captured once and replayed; per-step inputs (step scalars, timestep, origin feature,
     noise) are refreshed in static device buffers before each replay."""
 
-    def __init__(self, model, diffusion, geometry: DragGeometry, feat_layer, cof, loss_type, scale,
+    def __init__(self, model, diffusion, geometry, feat_layer, cof, loss_type, scale,
                  clip_denoised=True, use_graph=True, overlap_tail=True):
+        """`geometry`: one DragGeometry (the reference's batch-1 edit) or a list of B geometries with the same
+        number of handles — B independent edits advanced together as one batch-B UNet pass (the "batched"
+        variant of SURVEY.md §8d config 5; the reference itself refuses num_samples > 1, drag_utils.py:303)."""
         self.model, self.diffusion = model, diffusion
-        self.plan = model.plan(1, model.image_size, model.image_size, want_backward=True)
+        geos = list(geometry) if isinstance(geometry, (list, tuple)) else [geometry]
+        B = self.batch = len(geos)
+        assert all(g.npts == geos[0].npts and g.group_size == geos[0].group_size for g in geos)
+        self.plan = model.plan(B, model.image_size, model.image_size, want_backward=True)
         ops = self.ops = self.plan.ops
         dev = ops.device
-        self.geo = geometry.to(dev)
-        self.dyn = th.tensor([geometry.inv_count, 1.0 / (max(geometry.mask_count, 1))], dtype=th.float32, device=dev)
         self.feat_layer, self.cof, self.scale, self.clip = feat_layer, float(cof), float(scale), clip_denoised
         self.loss_type = 1 if loss_type == "l1" else 0
         inter = self.plan.block_out[feat_layer]
         _, S, _, Cf = inter.val.shape
         chan_map, inv_map, Ca = align_maps(Cf)
         self.chan_map, self.inv_map, self.S, self.Cf, self.Ca = chan_map.to(dev), inv_map.to(dev), S, Cf, Ca
+        self.geos = [g.to(dev) for g in geos]
+        self.dyns = [th.tensor([g.inv_count, 1.0 / (max(g.mask_count, 1) * Ca)], dtype=th.float32, device=dev)
+                     for g in geos]
+        self.geo, self.dyn = self.geos[0], self.dyns[0]
         C, R = model.in_channels, model.image_size
-        self.img = ops.empty((1, C, R, R))
-        self.img_next = ops.empty((1, C, R, R))
-        self.noise = ops.empty((1, C, R, R))
-        self.grad = ops.empty((1, C, R, R))
-        self.variance = ops.empty((1, C, R, R))
-        self.sample = ops.empty((1, C, R, R))
-        self.origin = ops.empty((3, S, S, Ca))
+        self.img = ops.empty((B, C, R, R))
+        self.img_next = ops.empty((B, C, R, R))
+        self.noise = ops.empty((B, C, R, R))
+        self.grad = ops.empty((B, C, R, R))
+        self.variance = ops.empty((B, C, R, R))
+        self.sample = ops.empty((B, C, R, R))
+        self.origin = ops.empty((B, 3, S, S, Ca)) if B > 1 else ops.empty((3, S, S, Ca))
         self.coef = ops.empty((8,))
         self.coef_table = diffusion.coef_table(dev, guide_scale=self.scale)
         tmap = getattr(diffusion, "timestep_map", list(range(diffusion.num_timesteps)))
         self.t_table = th.tensor(tmap, device=dev, dtype=th.int64)
         npts = self.geo.npts
-        self.g = ops.empty((3, npts, Ca))
-        self.pt_info = ops.empty((3, npts, 4))
-        self.partial = ops.zeros((ops.drag_partial_len(S, Cf, npts),), th.float64)
-        self.loss = ops.zeros((1,))
+        self.g = ops.empty((B, 3, npts, Ca))
+        self.pt_info = ops.empty((B, 3, npts, 4))
+        self.partial = ops.zeros((B, ops.drag_partial_len(S, Cf, npts)), th.float64)
+        self.loss = ops.zeros((B,))
         self.plan.ensure_grad(inter)
-        self.dyn[1] /= Ca
         self.use_graph = use_graph and dev.type == "cuda"
         self.overlap_tail = overlap_tail
         if dev.type == "cuda":
@@ -247,10 +254,13 @@ class GuidedStepper:
                 self._side.wait_event(self._ev_fork)
                 plan.forward_tail()
                 self._ev_join.record(self._side)
-        ops.drag_loss_grad(inter.val, self.origin, self.chan_map, self.inv_map, geo.patch_xy, geo.shift_xy,
-                           geo.weight, geo.group_size, geo.bbox, geo.mask, geo.mask_count, geo.inv_count,
-                           self.cof, self.loss_type, self.g, self.pt_info, self.partial, self.loss, inter.grad,
-                           dyn=self.dyn)
+        for b in range(self.batch):           # the drag loss couples nothing across edits: one small launch set each
+            geo = self.geos[b]
+            origin = self.origin[b] if self.batch > 1 else self.origin
+            ops.drag_loss_grad(inter.val[b:b + 1], origin, self.chan_map, self.inv_map, geo.patch_xy, geo.shift_xy,
+                               geo.weight, geo.group_size, geo.bbox, geo.mask, geo.mask_count, geo.inv_count,
+                               self.cof, self.loss_type, self.g[b], self.pt_info[b], self.partial[b],
+                               self.loss[b:b + 1], inter.grad[b:b + 1], dyn=self.dyns[b])
         plan.begin_backward()
         plan.seed_grad(inter)
         plan.backward(self.grad)
@@ -263,7 +273,7 @@ class GuidedStepper:
     def step(self, i, origin_feature, noise=None):
         """Advance self.img from respaced step i to i-1.  origin_feature: (3,S,S,Ca) device tensor."""
         self.coef.copy_(self.coef_table[i])
-        self.plan.t_dev.copy_(self.t_table[i:i + 1])
+        self.plan.t_dev.copy_(self.t_table[i:i + 1].expand(self.batch))
         self.origin.copy_(origin_feature)
         if noise is None:
             self.noise.normal_()

@@ -212,3 +212,28 @@ def test_guided_step_and_training_generator(small):
     next(gen)
     ds.train_flag = False           # the GUI's stop button (main.py:485)
     assert list(gen) == [] and seen["t"] == 2
+
+
+def test_batched_guided_step_equals_independent_edits(small):
+    """B edits advanced as one batch-B pass == the same edits advanced one by one (edits are independent,
+    SURVEY.md §8e): plan batch handling, per-edit drag geometry and per-edit origin features."""
+    from ishapediting_b200.drag_utils import DragGeometry, GuidedStepper
+
+    cfg, sd, model, diff = small
+    sched = O.Schedule(1000, "200")
+    g, x, x2, noise = seeded_inputs(cfg)
+    i = 20
+    xs = [x, x2]
+    refs, geos, origins = [], [], []
+    for b in range(2):
+        origin, src, tgt, r1, voxel, pg, sg, masks = drag_problem(cfg, sd, sched, xs[1 - b], noise, i, g, r1=3, voxel=2.0 / 64)
+        refs.append(O.guided_step(sd, cfg, sched, xs[b], i, origin, noise, pg, sg, masks, scale=600.0, cof=0.2))
+        geos.append(DragGeometry(src, tgt, r1, voxel, origin.shape[-1], origin.shape[1]))
+        origins.append(origin.permute(0, 2, 3, 1).contiguous())
+    st = GuidedStepper(model, diff, geos, 8, 0.2, "l2", 600.0, use_graph=False)
+    st.img.copy_(torch.cat(xs))
+    st.step(i, torch.stack(origins), torch.cat([noise, noise]))
+    for b in range(2):
+        assert rel_l2(st.grad[b:b + 1], refs[b]["grad"]) < 1e-5
+        assert rel_l2(st.img[b:b + 1], refs[b]["img"]) < 1e-6
+        assert abs(float(st.loss[b]) - float(refs[b]["loss"])) < 1e-5 * abs(float(refs[b]["loss"]))
