@@ -90,6 +90,7 @@ typedef struct isb_conv_desc {
   int split_k;
   int stages;
   int w_tiled;           /* 1: w is panel-tiled (see above); needs Cout % 64 == 0 */
+  int two_cta;           /* 0 heuristic, 1 force the CTA-pair (cta_group::2) kernel, 2 forbid it */
 } isb_conv_desc;
 /* Workspace (split-K partial tiles + arrival counters): must be ZERO-FILLED by the caller before its
  * first use; every launch leaves the counters at zero again, so one buffer serves all layers. */

@@ -34,6 +34,7 @@ struct TcParams {
   int Cin, chunks0, ntaps, chunks1;
   int k_iters, splits, stages;
   int w_tiled;     // 1: weights packed as [Cout/64][K/64][64][64] panels (8 KiB contiguous per TMA box row-group)
+  int two_cta;     // 1: CTA pair (cta_group::2): 256-row MMA, each CTA stages its A half and half of the B tile
   int cluster;     // 1: the `splits` CTAs of an output tile form a thread-block cluster (DSMEM reduce)
   int tmem_cols;
   const float* bias;
@@ -161,6 +162,53 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t laddr, uint32_t rank) {
                : "r"(raddr)
                : "memory");
   return v;
+}
+
+// ---- CTA-pair (cta_group::2) helpers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads issued by either CTA of the pair; completion bytes are credited to the LEADER's mbarrier
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(m), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(m), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (when all MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_pair(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 
 // bias + residual (+ previous out) and store 8 consecutive output channels
@@ -480,6 +528,161 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
+// ---- CTA-pair kernel: two SMs of one TPC cooperate on a 256 x block_n output tile ---------------
+// (cta_group::2).  Each CTA stages its own 128 pixel rows of A and HALF of the B (weight) tile, so the
+// shared-memory fill per FLOP — what bounds the single-CTA kernel on the 64^2 / 128^2 layers
+// (profiles/r01_ncu_full_conv_tc.md) — drops by 1/3 (block_n = 128) to 1/2 (block_n = 256).  The leader CTA's
+// MMA thread issues tcgen05.mma.cta_group::2 for the pair; TMA completions from both CTAs are credited to the
+// leader's "full" barrier; tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
+                const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
+  const int half_n = p.block_n / 2;
+  const uint32_t stage_bytes = TC_A_STAGE + static_cast<uint32_t>(half_n) * 128u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  int mt = blockIdx.x;
+  const int tile_w = mt % p.tiles_w;
+  mt /= p.tiles_w;
+  const int tile_h = mt % p.tiles_h;
+  const int tile_n = mt / p.tiles_h;
+  const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.nb;
+  const int cout0 = blockIdx.y * p.block_n;
+  const int niter = p.k_iters;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapA2);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 2);    // leader's arrive.expect_tx + the peer's remote arrive
+      mbar_init(smem_u32(&empty_bar[s]), 1);   // one multicast commit per phase
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();     // barriers of both CTAs initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      const int seg0_iters = p.ntaps * p.chunks0;
+      pdl_wait();
+      for (int i = 0; i < niter; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = static_cast<uint32_t>(i / p.stages) & 1u;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t fb_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
+        if (leader) mbar_expect_tx(smem_u32(&full_bar[s]), 2u * stage_bytes);
+        else mbar_arrive_cluster(fb_leader);
+        const uint32_t a_dst = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
+        const uint32_t b_dst = a_dst + TC_A_STAGE;
+        const int brow = cout0 + static_cast<int>(rank) * half_n;
+        if (i < seg0_iters) {
+          const int tap = i / p.chunks0;
+          const int chunk = i - tap * p.chunks0;
+          int dh = 0, dw = 0;
+          if (p.ntaps == 9) {
+            dh = tap / 3 - 1;
+            dw = tap % 3 - 1;
+          }
+          tma2_load_4d(a_dst, &mapA, fb_leader, chunk * TC_BLOCK_K, w0 + dw, h0 + dh, n0);
+          tma2_load_2d(b_dst, &mapB, fb_leader, tap * p.Cin + chunk * TC_BLOCK_K, brow);
+        } else {
+          const int chunk = i - seg0_iters;
+          tma2_load_4d(a_dst, &mapA2, fb_leader, chunk * TC_BLOCK_K, w0, h0, n0);
+          tma2_load_2d(b_dst, &mapB, fb_leader, p.ntaps * p.Cin + chunk * TC_BLOCK_K, brow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only, one thread for the pair =====
+    if (leader && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                             (static_cast<uint32_t>(p.block_n >> 3) << 17) |
+                             (static_cast<uint32_t>(256 >> 4) << 24);
+      for (int i = 0; i < niter; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = static_cast<uint32_t>(i / p.stages) & 1u;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t a_addr = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
+        const uint64_t adesc = make_desc_sw128(a_addr);
+        const uint64_t bdesc = make_desc_sw128(a_addr + TC_A_STAGE);
+#pragma unroll
+        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+          umma2_bf16(tmem_base, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                     (i > 0 || k > 0) ? 1u : 0u);
+        umma2_commit_pair(smem_u32(&empty_bar[s]));
+      }
+      umma2_commit_pair(smem_u32(&tmem_full_bar));
+    }
+  } else {
+    // ===== epilogue warps 2..5 (both CTAs, each its own 128 rows) =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int per_img = p.tw * p.th;
+    const int pn = r / per_img;
+    const int rem = r - pn * per_img;
+    const int ph_ = rem / p.tw;
+    const int pw_ = rem - ph_ * p.tw;
+    const int n = n0 + pn;
+    const bool valid = n < p.N;
+    const size_t m = (static_cast<size_t>(n) * p.H + (h0 + ph_)) * p.W + (w0 + pw_);
+    const int nchunks = p.block_n / 32;
+    mbar_wait(smem_u32(&tmem_full_bar), 0);
+    tc_fence_after();
+    pdl_wait();
+    for (int c = 0; c < nchunks; ++c) {
+      const int col0 = cout0 + c * 32;
+      if (col0 >= p.Cout) break;
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
+      tmem_ld_wait();
+      if (!valid) continue;
+      const size_t off = m * p.Cout + col0;
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
+        epilogue_store8(p, f, off + j8 * 8, col0 + j8 * 8);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();     // the pair's TMEM is released together; nobody exits while the peer still needs its smem
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(p.tmem_cols))
+                 : "memory");
+  }
+}
+
 // ---- host side --------------------------------------------------------------
 struct TcPlan {
   TcParams p;
@@ -543,17 +746,39 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   ISB_CHECK_ARG(bn >= 32 && bn <= 256 && bn % 32 == 0, "conv_tc: block_n=%d must be a multiple of 32 in [32,256]", bn);
   p.block_n = bn;
   p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
-  const int ntiles = cdiv(d->Cout, bn);
-  const int tiles = mtiles * ntiles;
+  int ntiles = cdiv(d->Cout, bn);
+  int tiles = mtiles * ntiles;
   int splits = d->split_k ? d->split_k : splits_for(tiles);
   ISB_CHECK_ARG(splits >= 1 && splits <= p.k_iters, "conv_tc: split_k=%d out of range (k_iters=%d)", splits, p.k_iters);
   p.splits = splits;
   p.cluster = (splits == 2 || splits == 4 || splits == 8) ? 1 : 0;   // other counts: workspace fold
-  const int stage_bytes = TC_A_STAGE + bn * 128;
+  // CTA pairs for the big, un-split layers: 256-wide N tile, both m-tiles of a pair share the weight tile
+  int two = d->two_cta;
+  if (two == 0 && d->block_n == 0 && splits == 1 && mtiles % 2 == 0 && d->Cout % 256 == 0 &&
+      static_cast<long long>(mtiles) * (d->Cout / 256) >= sms / 2) {
+    two = 1;
+    bn = 256;
+    p.block_n = bn;
+    p.tmem_cols = 256;
+  }
+  if (two != 1) two = 0;
+  if (two) {
+    ISB_CHECK_ARG(splits == 1 && mtiles % 2 == 0 && (bn == 128 || bn == 256) && d->Cout % bn == 0,
+                  "conv_tc: CTA-pair mode needs split_k=1, an even number of pixel tiles (%d) and block_n 128/256 dividing Cout", mtiles);
+    ISB_CHECK_ARG(!d->w_tiled, "conv_tc: CTA-pair mode uses row-major weights");
+  }
+  p.two_cta = two;
+  if (p.two_cta) {
+    ntiles = cdiv(d->Cout, bn);
+    tiles = mtiles * ntiles;
+  }
+  const int stage_bytes = TC_A_STAGE + (p.two_cta ? bn / 2 : bn) * 128;
   const int max_stages = (TC_SMEM_LIMIT - 1024) / stage_bytes;
   int stages = d->stages;
   if (stages == 0) {
-    if (static_cast<long long>(tiles) * splits <= sms) {
+    if (p.two_cta) {
+      stages = 5;
+    } else if (static_cast<long long>(tiles) * splits <= sms) {
       stages = 6;                                   // alone on its SM: prefetch as deep as smem allows
       const int per_cta = cdiv(p.k_iters, splits);
       if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
@@ -639,6 +864,7 @@ static int encode_weight_map_tiled(CUtensorMap* m, const void* ptr, int Cout, in
 
 int conv_tc_init() {
   ISB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+  ISB_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
   return ISB_OK;
 }
 
@@ -680,7 +906,7 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
     ISB_CHECK_ARG(d->Cout % 64 == 0 && p.block_n % 64 == 0, "conv_tc: panel-tiled weights need Cout %% 64 == 0 and block_n %% 64 == 0 (Cout=%d, block_n=%d)", d->Cout, p.block_n);
     rc = encode_weight_map_tiled(&mapB, d->w, d->Cout, Ktot, p.block_n);
   } else {
-    rc = encode_weight_map(&mapB, d->w, d->Cout, Ktot, p.block_n);
+    rc = encode_weight_map(&mapB, d->w, d->Cout, Ktot, p.two_cta ? p.block_n / 2 : p.block_n);
   }
   if (rc) return rc;
   cudaLaunchConfig_t cfg = {};
@@ -695,16 +921,17 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (p.cluster) {
+  if (p.cluster || p.two_cta) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.x = p.two_cta ? 2 : 1;
     attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = p.splits;
+    attr[na].val.clusterDim.z = p.two_cta ? 1 : p.splits;
     ++na;
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  ISB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, mapA, mapA2, mapB, p));
+  if (p.two_cta) ISB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel, mapA, mapA2, mapB, p));
+  else ISB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, mapA, mapA2, mapB, p));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }

@@ -19,6 +19,11 @@ CASES = [
     ("k3_32x32_128_128_cl2", 1, 32, 32, 128, 128, 3, 0, True, True, False, False, {"split_k": 2}),
     ("k3_16x16_256_256_cl4", 1, 16, 16, 256, 256, 3, 0, True, False, True, False, {"split_k": 4, "block_n": 128}),
     ("k3_16x16_256_256_cl8_bn256", 1, 16, 16, 256, 256, 3, 0, True, True, False, False, {"split_k": 8, "block_n": 256}),
+    # CTA pairs (cta_group::2): 256-row MMA, B tile split across the two CTAs
+    ("k3_32x32_128_256_pair", 1, 32, 32, 128, 256, 3, 0, True, True, False, False, {"two_cta": 1, "block_n": 256, "split_k": 1}),
+    ("k3_64x64_64_128_pair_bn128", 1, 64, 64, 64, 128, 3, 0, True, False, False, True, {"two_cta": 1, "block_n": 128, "split_k": 1}),
+    ("k3_16x16_n2_128_512_pair_skip", 2, 16, 16, 128, 512, 3, 64, True, False, True, False, {"two_cta": 1, "block_n": 256, "split_k": 1}),
+    ("k1_128x128_64_256_pair", 1, 128, 128, 64, 256, 1, 0, False, True, False, False, {"two_cta": 1, "block_n": 256, "split_k": 1}),
     ("k1_8x8_1024_1024_auto", 1, 8, 8, 1024, 1024, 1, 0, True, True, False, True, None),
     ("k3_8x8_1024_1024_auto", 1, 8, 8, 1024, 1024, 3, 0, True, False, False, False, None),
 ]
