@@ -73,13 +73,18 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a pipeline bug must trap (CUDA error to the caller), never hang the GPU.
+// Bounded wait: a pipeline bug must trap (CUDA error to the caller), never hang the GPU.  The fast path is
+// a bare try_wait loop (the instruction itself suspends the thread for a HW time slice); the SM cycle
+// counter is consulted only every 4096 failed probes — no %globaltimer reads on the critical path.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0 && global_timer_ns() - t0 > 2000000000ull) __trap();
+    if ((++spins & 0xfffu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 6000000000ll) __trap();   // ~3 s at 1.9 GHz
+    }
   }
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
@@ -754,12 +759,11 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   p.cluster = (splits == 2 || splits == 4 || splits == 8) ? 1 : 0;   // other counts: workspace fold
   // CTA pairs for the big, un-split layers: 256-wide N tile, both m-tiles of a pair share the weight tile
   int two = d->two_cta;
-  if (two == 0 && d->block_n == 0 && splits == 1 && mtiles % 2 == 0 && d->Cout % 256 == 0 &&
-      static_cast<long long>(mtiles) * (d->Cout / 256) >= sms / 2) {
-    two = 1;
-    bn = 256;
+  if (two == 0 && d->block_n == 0 && splits == 1 && mtiles % 2 == 0 && mtiles >= 64 && d->Cout % 128 == 0 && !d->w_tiled) {
+    two = 1;          // sweep (profiles/r01_conv_tune_pair.txt): pairs with 128-wide tiles, 4 stages, two pairs' CTAs per SM
+    bn = 128;
     p.block_n = bn;
-    p.tmem_cols = 256;
+    p.tmem_cols = 128;
   }
   if (two != 1) two = 0;
   if (two) {
@@ -777,7 +781,7 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   int stages = d->stages;
   if (stages == 0) {
     if (p.two_cta) {
-      stages = 5;
+      stages = bn <= 128 ? 4 : 5;
     } else if (static_cast<long long>(tiles) * splits <= sms) {
       stages = 6;                                   // alone on its SM: prefetch as deep as smem allows
       const int per_cta = cdiv(p.k_iters, splits);

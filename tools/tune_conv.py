@@ -12,6 +12,8 @@ import torch
 from ishapediting_b200.ops import CudaOps, PackedWeight
 from ishapediting_b200._lib import IsbError
 
+SHAPES_BIG = [(32, 3, 512, 512), (32, 3, 768, 768), (64, 3, 256, 256), (64, 3, 512, 512), (64, 3, 512, 256),
+              (128, 3, 256, 256), (128, 3, 512, 256), (128, 3, 128, 256)]
 SHAPES = [  # H(=W), ksize, Cin, Cout
     (8, 3, 1024, 1024), (8, 1, 1024, 1024), (8, 1, 3072, 1024), (8, 1, 1024, 3072),
     (16, 3, 768, 768), (16, 3, 1024, 1024), (16, 1, 768, 768), (16, 1, 768, 2304),
@@ -49,10 +51,11 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--warm", action="store_true", help="one weight copy: weights stay L2-resident")
     ap.add_argument("--auto-only", action="store_true")
+    ap.add_argument("--big", action="store_true")
     args = ap.parse_args()
     ops = CudaOps(torch.device("cuda", 0), "bf16")
     dev = ops.device
-    for (H, k, Cin, Cout) in SHAPES:
+    for (H, k, Cin, Cout) in (SHAPES_BIG if args.big else SHAPES):
         K = k * k * Cin
         wbytes = Cout * K * 2
         ncopies = max(4, min(64, int(400e6 // wbytes)))           # ring > L2 (126 MB) when weights are big
@@ -77,6 +80,12 @@ def main():
             t, err = bench(ops, a, base, bias, k, out, {"block_n": bn, "split_k": sp, "stages": stg}, False)
             if t is not None:
                 rows.append((t, bn, sp, stg))
+        if H >= 32 and Cout % 128 == 0:      # CTA-pair kernel (cta_group::2)
+            for bn in ([128, 256] if Cout % 256 == 0 else [128]):
+                for stg in (4, 5, 6):
+                    t, err = bench(ops, a, base, bias, k, out, {"block_n": bn, "split_k": 1, "stages": stg, "two_cta": 1}, False)
+                    if t is not None:
+                        rows.append((t, f"pair{bn}", 1, stg))
         rows.sort()
         best = rows[0]
         print(f"H={H:3d} k{k} {Cin:4d}->{Cout:4d}  auto {t_auto:7.1f} us | best {best[0]:7.1f} us bn={best[1]} split={best[2]} "
