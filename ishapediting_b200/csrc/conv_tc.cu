@@ -34,6 +34,7 @@ struct TcParams {
   int Cin, chunks0, ntaps, chunks1;
   int k_iters, splits, stages;
   int w_tiled;     // 1: weights packed as [Cout/64][K/64][64][64] panels (8 KiB contiguous per TMA box row-group)
+  int debug;       // profiling only: bit0 = producer skips the TMA loads, bit1 = MMA thread skips the MMAs
   int two_cta;     // 1: CTA pair (cta_group::2): 256-row MMA, each CTA stages its A half and half of the B tile
   int cluster;     // 1: the `splits` CTAs of an output tile form a thread-block cluster (DSMEM reduce)
   int tmem_cols;
@@ -335,19 +336,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       };
       // The weight panels never change during a step: start streaming them into the ring before the
       // producer of our activations has even finished (PDL), then wait and fetch the activations.
+      const bool skip_tma = (p.debug & 1) != 0;
       for (int i = 0; i < npre; ++i) {
-        mbar_expect_tx(smem_u32(&full_bar[i]), stage_bytes);
-        load_b(i);
+        mbar_expect_tx(smem_u32(&full_bar[i]), skip_tma ? 0u : stage_bytes);
+        if (!skip_tma) load_b(i);
       }
       pdl_wait();
-      for (int i = 0; i < npre; ++i) load_a(i);
+      if (!skip_tma)
+        for (int i = 0; i < npre; ++i) load_a(i);
       for (int i = npre; i < niter; ++i) {
         const int s = i % p.stages;
         const uint32_t ph = static_cast<uint32_t>(i / p.stages) & 1u;
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-        mbar_expect_tx(smem_u32(&full_bar[s]), stage_bytes);
-        load_a(i);
-        load_b(i);
+        mbar_expect_tx(smem_u32(&full_bar[s]), skip_tma ? 0u : stage_bytes);
+        if (!skip_tma) {
+          load_a(i);
+          load_b(i);
+        }
       }
     }
   } else if (warp == 1) {
@@ -366,11 +371,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t a_addr = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
         const uint64_t adesc = make_desc_sw128(a_addr);
         const uint64_t bdesc = make_desc_sw128(a_addr + TC_A_STAGE);
+        if (!(p.debug & 2)) {
 #pragma unroll
-        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-          // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
-          umma_bf16(tmem_base, adesc + static_cast<uint64_t>(k * 2),
-                    bdesc + static_cast<uint64_t>(k * 2), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
+            umma_bf16(tmem_base, adesc + static_cast<uint64_t>(k * 2),
+                      bdesc + static_cast<uint64_t>(k * 2), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(smem_u32(&empty_bar[s]));  // frees the smem slot when these MMAs retire
       }
@@ -778,7 +785,7 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   }
   const int stage_bytes = TC_A_STAGE + (p.two_cta ? bn / 2 : bn) * 128;
   const int max_stages = (TC_SMEM_LIMIT - 1024) / stage_bytes;
-  int stages = d->stages;
+  int stages = d->stages % 100;
   if (stages == 0) {
     if (p.two_cta) {
       stages = bn <= 128 ? 4 : 5;
@@ -809,6 +816,7 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   p.partial = nullptr;
   p.counters = nullptr;
   p.w_tiled = d->w_tiled;
+  p.debug = d->stages >= 100 ? d->stages / 100 : 0;   // profiling hook: stages = 100*debug + stages
   return ISB_OK;
 }
 
