@@ -200,6 +200,7 @@ typedef struct isb_ddpm_desc {
   const float* coef;  /* device [8] */
   int N, C, H, W; int clip_denoised;
   float* x_next; float* sample; float* mean; float* var; float* x0; float* eps;
+  int coef_per_sample;  /* 1: coef is [N][8], one row per batch element (batched DDPM inversion) */
 } isb_ddpm_desc;
 int isb_ddpm_step(const isb_ddpm_desc* d, isb_stream_t stream);
 

@@ -68,7 +68,7 @@ class DdpmDesc(C.Structure):
         ("noise", c_void_p), ("grad", c_void_p), ("coef", c_void_p),
         ("N", c_int), ("C", c_int), ("H", c_int), ("W", c_int), ("clip_denoised", c_int),
         ("x_next", c_void_p), ("sample", c_void_p), ("mean", c_void_p), ("var", c_void_p),
-        ("x0", c_void_p), ("eps", c_void_p),
+        ("x0", c_void_p), ("eps", c_void_p), ("coef_per_sample", c_int),
     ]
 
 

@@ -12,7 +12,7 @@ namespace isb {
 
 struct DdpmArgs {
   const float* x; const float* mo; int cstride; int mo_nchw;
-  const float* noise; const float* grad; const float* coef;
+  const float* noise; const float* grad; const float* coef; int coef_stride;
   int C, HW; int clip;
   float* x_next; float* sample; float* mean; float* var; float* x0; float* eps;
 };
@@ -40,10 +40,11 @@ ddpm_step_kernel(const DdpmArgs a) {
     t_v[ty + i * 8][tx] = v;
   }
   __syncthreads();
-  const float sra = a.coef[ISB_SC_SQRT_RECIP_ACP], srm1 = a.coef[ISB_SC_SQRT_RECIPM1_ACP];
-  const float c1 = a.coef[ISB_SC_POST_COEF1], c2 = a.coef[ISB_SC_POST_COEF2];
-  const float min_log = a.coef[ISB_SC_MIN_LOG], max_log = a.coef[ISB_SC_MAX_LOG];
-  const float nonzero = a.coef[ISB_SC_NONZERO], gscale = a.coef[ISB_SC_GUIDE_SCALE];
+  const float* cf = a.coef + static_cast<size_t>(n) * a.coef_stride;   // per-sample rows when coef_stride = 8
+  const float sra = cf[ISB_SC_SQRT_RECIP_ACP], srm1 = cf[ISB_SC_SQRT_RECIPM1_ACP];
+  const float c1 = cf[ISB_SC_POST_COEF1], c2 = cf[ISB_SC_POST_COEF2];
+  const float min_log = cf[ISB_SC_MIN_LOG], max_log = cf[ISB_SC_MAX_LOG];
+  const float nonzero = cf[ISB_SC_NONZERO], gscale = cf[ISB_SC_GUIDE_SCALE];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = c0 + ty + i * 8, p = p0 + tx;
@@ -83,7 +84,7 @@ extern "C" {
 int isb_ddpm_step(const isb_ddpm_desc* d, isb_stream_t stream) {
   ISB_CHECK_ARG(d && d->x && d->model_out && d->coef, "isb_ddpm_step: null pointer");
   ISB_CHECK_ARG(d->N > 0 && d->C > 0 && d->H > 0 && d->W > 0 && (d->model_out_nchw || d->model_out_cstride >= 2 * d->C), "isb_ddpm_step: bad shape");
-  isb::DdpmArgs a{d->x, d->model_out, d->model_out_cstride, d->model_out_nchw, d->noise, d->grad, d->coef,
+  isb::DdpmArgs a{d->x, d->model_out, d->model_out_cstride, d->model_out_nchw, d->noise, d->grad, d->coef, d->coef_per_sample ? 8 : 0,
                   d->C, d->H * d->W, d->clip_denoised,
                   d->x_next, d->sample, d->mean, d->var, d->x0, d->eps};
   dim3 grid(isb::cdiv(a.HW, 32), isb::cdiv(a.C, 32), d->N);

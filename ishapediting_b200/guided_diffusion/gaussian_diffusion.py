@@ -143,10 +143,7 @@ class GaussianDiffusion:
                                       "ModelVarType.LEARNED_RANGE (the NFD configuration, learn_sigma=True)")
         if denoised_fn is not None:
             raise NotImplementedError("denoised_fn is not supported by the fused update")
-        ti = [int(v) for v in t.tolist()]
-        if any(v != ti[0] for v in ti):
-            raise NotImplementedError("all batch elements must share one step index (the editor's loops do)")
-        return ti[0]
+        return None
 
     def p_mean_variance(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None, feat_layer=-1):
         """Reference :232-331.  The UNet runs through the plan; eps/variance/x0/mean come from ONE fused
@@ -156,7 +153,7 @@ class GaussianDiffusion:
         model_kwargs = model_kwargs or {}
         B, C = x.shape[:2]
         assert t.shape == (B,)
-        i = self._check_supported(t, denoised_fn)
+        self._check_supported(t, denoised_fn)
         if feat_layer < 0:
             model_output, inter_feat = model(x, self._scale_timesteps(t), **model_kwargs), None
         else:
@@ -178,7 +175,8 @@ class GaussianDiffusion:
         ops = _ops_of(model)
         xd = x.detach().to(th.float32).contiguous()
         mean, var, x0, eps = (th.empty_like(xd) for _ in range(4))
-        ops.ddpm_step(xd, model_output.detach().contiguous(), self.coef_table(x.device)[i].contiguous(), clip_denoised,
+        coef = self.coef_table(x.device)[t.to(x.device)].contiguous()      # [B,8]: one schedule row per batch element
+        ops.ddpm_step(xd, model_output.detach().contiguous(), coef, clip_denoised,
                       mean=mean, var=var, x0=x0, eps=eps)
         return {"mean": mean, "variance": var, "log_variance": th.log(var), "pred_xstart": x0,
                 "inter_feat": inter_feat, "model_output": eps}
@@ -209,25 +207,33 @@ class GaussianDiffusion:
         return {"sample": sample, "pred_xstart": out["pred_xstart"], "inter_feat": out["inter_feat"],
                 "model_output": out["model_output"], "noise": noise, "variance": var_used, "mean": out["mean"]}
 
-    def ddpm_inversion(self, model, x_0, steps, **kwargs):
-        """Reference :512-532: forward noising chain, then per-step z_i = x_i - mean_i."""
-        feat, variance_noise, variance = [], [], []
+    def ddpm_inversion(self, model, x_0, steps, batch=8, **kwargs):
+        """Reference :512-532: forward noising chain, then per-step z_i = x_i - mean_i.  The reverse-pass UNet
+        evaluations are mutually independent (each input is a pre-drawn x_{i+1}), so they run `batch` at a time as
+        one batch-B pass with per-sample timesteps and schedule rows; results and their order
+        are the reference's."""
+        assert x_0.shape[0] == 1, "the editor inverts one shape at a time (drag_utils.py:552-566)"
+        feat, variance_noise, variance = [None] * steps, [None] * steps, [None] * steps
         with th.no_grad():
             img_inter = [x_0]
             for i in range(0, steps):
-                cof = float(self.alphas_cumprod[i]) / float(self.alphas_cumprod_prev[i])
                 cof = th.tensor(np.float32(self.alphas_cumprod[i]), device=x_0.device) / \
                     th.tensor(np.float32(self.alphas_cumprod_prev[i]), device=x_0.device)
                 x_0 = th.sqrt(cof) * x_0 + th.sqrt(1 - cof) * th.randn_like(x_0)
                 img_inter.append(x_0)
-            img = img_inter[-1]
-            for i in range(steps - 1, -1, -1):
-                t = th.tensor([i] * img.shape[0], device=img.device)
-                outs = self.p_sample_guidance(model, img, t, **kwargs)
-                variance.append(outs["variance"])
-                feat.append(outs["inter_feat"])
-                variance_noise.append(img_inter[i] - outs["mean"])
-                img = outs["mean"] + variance_noise[-1]
+            order = list(range(steps - 1, -1, -1))
+            for c0 in range(0, steps, batch):
+                idx = order[c0:c0 + batch]
+                xb = th.cat([img_inter[i + 1] for i in idx], dim=0)
+                t = th.tensor(idx, device=xb.device)
+                outs = self.p_sample_guidance(model, xb, t, noise=th.zeros_like(xb), **kwargs)
+                for k, i in enumerate(idx):
+                    pos = steps - 1 - i
+                    variance[pos] = outs["variance"][k:k + 1]
+                    feat[pos] = outs["inter_feat"][k:k + 1] if outs["inter_feat"] is not None else None
+                    variance_noise[pos] = img_inter[i] - outs["mean"][k:k + 1]
+                    if i == 0:
+                        img = outs["mean"][k:k + 1] + variance_noise[pos]     # (:531) == x_0 up to one rounding
         return {"inter_feat": feat, "latent": img_inter[-1], "variance_noise": variance_noise, "variance": variance,
                 "sample": img}
 

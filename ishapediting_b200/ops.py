@@ -256,6 +256,9 @@ class CudaOps:
         d.noise, d.grad, d.coef = _p(noise), _p(grad), _p(coef)
         d.N, d.C, d.H, d.W, d.clip_denoised = N, Cc, H, W, int(clip_denoised)
         d.x_next, d.sample, d.mean, d.var, d.x0, d.eps = _p(x_next), _p(sample), _p(mean), _p(var), _p(x0), _p(eps)
+        if coef.dim() == 2:
+            assert coef.shape == (N, 8)
+            d.coef_per_sample = 1
         _lib.check(self.lib.isb_ddpm_step(C.byref(d), _stream()), "isb_ddpm_step")
 
     # ---- drag guidance --------------------------------------------------------------------

@@ -173,7 +173,7 @@ class RefOps:
         C = x.shape[1]
         mo = model_out if (model_out.shape[1] == 2 * C and model_out.shape[2:] == x.shape[2:]) else _nchw(model_out)
         e, v = mo[:, :C], mo[:, C:2 * C]
-        c = coef
+        c = coef if coef.dim() == 1 else [coef[:, k].reshape(-1, 1, 1, 1) for k in range(8)]
         frac = (v + 1) / 2
         variance = torch.exp(frac * c[5] + (1 - frac) * c[4])
         xs = c[0] * x - c[1] * e

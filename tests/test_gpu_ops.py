@@ -168,6 +168,17 @@ def test_ddpm_step(ops, ref, nchw):
         r[name] = outs
     for k in names:
         assert rel_l2(r["cuda"][k], r["ref"][k]) < 1e-5, k
+    # per-sample schedule rows (batched DDPM inversion)
+    coef2 = torch.stack([coef, coef * torch.tensor([0.9, 1.1, 1.2, 0.8, 1.0, 1.0, 0.0, 1.0])])
+    r2 = {}
+    for name, o in (("ref", ref), ("cuda", ops)):
+        dev = "cpu" if name == "ref" else DEV
+        outs = {k: torch.zeros(N, C, H, W, device=dev) for k in names}
+        o.ddpm_step(x.to(dev), mo.to(dev), coef2.to(dev), True, noise=noise.to(dev), grad=grad.to(dev), **outs)
+        r2[name] = outs
+    for k in names:
+        assert rel_l2(r2["cuda"][k], r2["ref"][k]) < 1e-5, k
+    assert rel_l2(r2["cuda"]["x_next"][:1], r["cuda"]["x_next"][:1]) == 0.0
 
 
 def test_drag_loss_grad(ops, ref):

@@ -237,3 +237,30 @@ def test_batched_guided_step_equals_independent_edits(small):
         assert rel_l2(st.grad[b:b + 1], refs[b]["grad"]) < 1e-5
         assert rel_l2(st.img[b:b + 1], refs[b]["img"]) < 1e-6
         assert abs(float(st.loss[b]) - float(refs[b]["loss"])) < 1e-5 * abs(float(refs[b]["loss"]))
+
+
+def test_batched_ddpm_inversion_matches_stepwise_oracle(small):
+    """ddpm_inversion's reverse pass runs `batch` independent UNet evaluations at a time (per-sample timesteps
+    and schedule rows); every returned list must equal the step-by-step restatement
+    (gaussian_diffusion.py:512-532)."""
+    cfg, sd, model, diff = small
+    sched = O.Schedule(1000, "200")
+    g = torch.Generator().manual_seed(5)
+    x0 = (torch.randn(1, cfg["in_out_channels"], 32, 32, generator=g) * 0.5).clamp(-1, 1)
+    steps = 5
+    torch.manual_seed(123)
+    out = diff.ddpm_inversion(model, x0, steps, batch=2, clip_denoised=True, feat_layer=8)     # chunks 2,2,1
+    torch.manual_seed(123)
+    chain = [x0]
+    x = x0
+    for i in range(steps):
+        cof = torch.tensor(np.float32(sched.alphas_cumprod[i])) / torch.tensor(np.float32(sched.alphas_cumprod_prev[i]))
+        x = torch.sqrt(cof) * x + torch.sqrt(1 - cof) * torch.randn_like(x)
+        chain.append(x)
+    assert torch.equal(out["latent"], chain[-1])
+    for pos, i in enumerate(range(steps - 1, -1, -1)):
+        ref = O.p_sample_guidance(sd, cfg, sched, chain[i + 1], i, torch.zeros_like(x0), feat_layer=8)
+        assert rel_l2(out["inter_feat"][pos], ref["inter_feat"]) < 1e-5
+        assert rel_l2(out["variance"][pos], ref["variance"]) < 1e-5
+        assert float((out["variance_noise"][pos] - (chain[i] - ref["mean"])).abs().max()) < 1e-5
+    assert float((out["sample"] - x0).abs().max()) < 1e-6
