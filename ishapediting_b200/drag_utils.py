@@ -341,16 +341,48 @@ class DragStuff:
 
     # ---- no-grad trajectory + feature cache (reference :252-280) --------------------------------
     def _nograd_step(self, plan, img, i, feat_layer, noise=None):
-        """One unguided step on the plan; returns (img_next, inter _T)."""
+        """One unguided step (reference p_sample_guidance under no_grad, :267-271 / :289-293); returns
+        (img_next, inter _T).  On the GPU the step (UNet forward + fused posterior/sample) is captured once into
+        a CUDA graph per plan and replayed; step scalars, timestep, latent and noise live in static buffers."""
         ops = plan.ops
         dev = self.device
-        coef = self.diffusion.coef_table(dev)[i].contiguous()
+        st = getattr(plan, "_nograd_state", None)
+        if st is None:
+            st = plan._nograd_state = {
+                "img": ops.empty(tuple(img.shape)), "next": ops.empty(tuple(img.shape)),
+                "noise": ops.empty(tuple(img.shape)), "coef": ops.empty((8,)), "graph": None, "warm": 0,
+                "feat_layer": feat_layer}
         tmap = self.diffusion.timestep_map_tensor(dev)
-        inter = plan.forward(img, tmap[i:i + 1].contiguous(), feat_layer)
-        nz = th.randn_like(img) if noise is None else noise
-        nxt = th.empty_like(img)
-        ops.ddpm_step(img, plan.out_nhwc, coef, self.args.clip_denoised, noise=nz, x_next=nxt)
-        return nxt, inter
+        st["img"].copy_(img)
+        st["coef"].copy_(self.diffusion.coef_table(dev)[i])
+        plan.t_dev.copy_(tmap[i:i + 1].expand(plan.N))
+        if noise is None:
+            st["noise"].normal_()
+        else:
+            st["noise"].copy_(noise)
+
+        def body():
+            plan.forward(st["img"], plan.t_dev, feat_layer)
+            ops.ddpm_step(st["img"], plan.out_nhwc, st["coef"], self.args.clip_denoised, noise=st["noise"],
+                          x_next=st["next"])
+
+        use_graph = self.use_graph and dev.type == "cuda" and st["feat_layer"] == feat_layer
+        if not use_graph:
+            body()
+        elif st["graph"] is None:
+            if st["warm"] < 1:
+                st["warm"] += 1
+                body()
+            else:
+                g = th.cuda.CUDAGraph()
+                with th.cuda.graph(g):
+                    body()
+                st["graph"] = g
+                g.replay()
+        else:
+            st["graph"].replay()
+        inter = plan.block_out[feat_layer] if feat_layer >= 0 else None
+        return st["next"].clone(), inter
 
     def update_latent_params(self, img=None, **kwargs):
         dev = self.device
