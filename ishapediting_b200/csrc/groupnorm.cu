@@ -7,6 +7,7 @@
 // Reference: nn.py:16-18 (GroupNorm32, fp32 math), unet.py:183-184,207-208,245-253 (ResBlock
 // in/out layers with FiLM), unet.py:285 (attention norm), unet.py:613-614 (out), and
 // unet.py:107,136 (nearest 2x / avg-pool inside up/down ResBlocks).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace isb {
@@ -194,6 +195,42 @@ gn_apply_kernel(const GnArgs a, const GnFwdOut o) {
   gn_apply_one(a, o, n, h, w, c0, a.stats[(n * a.groups + g) * 2], a.stats[(n * a.groups + g) * 2 + 1]);
 }
 
+// ---- thread-block-cluster helpers (the fused kernels below run CS CTAs per (image, group)) -------------
+__device__ __forceinline__ uint32_t gn_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t gn_cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void gn_cluster_sync() {
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double gn_ld_dsmem_f64(const double* local, uint32_t rank) {
+  const uint32_t laddr = static_cast<uint32_t>(__cvta_generic_to_shared(local));
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(raddr) : "memory");
+  return v;
+}
+// block partials (thread 0 holds them) -> cluster totals in rank order (deterministic), returned to thread 0
+__device__ __forceinline__ void gn_cluster_fold(double* s_part, double& t0, double& t1) {
+  if (threadIdx.x == 0) { s_part[0] = t0; s_part[1] = t1; }
+  gn_cluster_sync();
+  if (threadIdx.x == 0) {
+    const uint32_t cs = gn_cluster_size();
+    double a0 = 0, a1 = 0;
+    for (uint32_t r = 0; r < cs; ++r) { a0 += gn_ld_dsmem_f64(s_part, r); a1 += gn_ld_dsmem_f64(s_part + 1, r); }
+    t0 = a0; t1 = a1;
+  }
+}
+
 // Small tensors: ONE launch, one CTA per (image, group): statistics pass, block reduction, apply pass
 // (the second read of the group's slice hits L1/L2).  Saves a launch and the global round trip.
 __global__ void __launch_bounds__(512)
@@ -201,12 +238,16 @@ gn_fused_fwd_kernel(const GnArgs a, const GnFwdOut o) {
   pdl_trigger();
   pdl_wait();
   __shared__ double sh0[16], sh1[16];
+  __shared__ double s_part[2];
   __shared__ float s_mean, s_rstd;
   const int g = blockIdx.x, n = blockIdx.y;
+  const int rank = static_cast<int>(gn_cluster_rank()), cs = static_cast<int>(gn_cluster_size());
   const int V = a.Cg / 8;
   const int total = a.HW * V;
+  const int beg = static_cast<int>(static_cast<long long>(total) * rank / cs);
+  const int end = static_cast<int>(static_cast<long long>(total) * (rank + 1) / cs);
   float s = 0.f, ss = 0.f;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
     float v[8];
     gn_load_x8(a, n, i / V, g * a.Cg + (i % V) * 8, v);
 #pragma unroll
@@ -215,26 +256,33 @@ gn_fused_fwd_kernel(const GnArgs a, const GnFwdOut o) {
   double d0 = warp_sum_d(static_cast<double>(s)), d1 = warp_sum_d(static_cast<double>(ss));
   if ((threadIdx.x & 31) == 0) { sh0[threadIdx.x >> 5] = d0; sh1[threadIdx.x >> 5] = d1; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double t0 = 0, t1 = 0;
+  double t0 = 0, t1 = 0;
+  if (threadIdx.x == 0)
     for (int w = 0; w < (blockDim.x >> 5); ++w) { t0 += sh0[w]; t1 += sh1[w]; }
+  gn_cluster_fold(s_part, t0, t1);
+  if (threadIdx.x == 0) {
     const double m = static_cast<double>(a.HW) * a.Cg;
     const double mean = t0 / m;
     double var = t1 / m - mean * mean;
     if (var < 0) var = 0;
     s_mean = static_cast<float>(mean);
     s_rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
-    a.stats[(n * a.groups + g) * 2 + 0] = s_mean;
-    a.stats[(n * a.groups + g) * 2 + 1] = s_rstd;
+    if (rank == 0) {
+      a.stats[(n * a.groups + g) * 2 + 0] = s_mean;
+      a.stats[(n * a.groups + g) * 2 + 1] = s_rstd;
+    }
   }
   __syncthreads();
   const float mean = s_mean, rstd = s_rstd;
   const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;
   const int total_o = Ho * Wo * V;
-  for (int i = threadIdx.x; i < total_o; i += blockDim.x) {
+  const int obeg = static_cast<int>(static_cast<long long>(total_o) * rank / cs);
+  const int oend = static_cast<int>(static_cast<long long>(total_o) * (rank + 1) / cs);
+  for (int i = obeg + threadIdx.x; i < oend; i += blockDim.x) {
     const int pix = i / V;
     gn_apply_one(a, o, n, pix / Wo, pix % Wo, g * a.Cg + (i % V) * 8, mean, rstd);
   }
+  gn_cluster_sync();   // peers may still be reading this CTA's partials
 }
 
 // ---- backward ---------------------------------------------------------------
@@ -366,13 +414,17 @@ gn_fused_bwd_kernel(const GnArgs a, const GnBwdArgs b) {
   pdl_trigger();
   pdl_wait();
   __shared__ double sh0[16], sh1[16];
+  __shared__ double s_part[2];
   __shared__ float s_m1, s_m2;
   const int g = blockIdx.x, n = blockIdx.y;
+  const int rank = static_cast<int>(gn_cluster_rank()), cs = static_cast<int>(gn_cluster_size());
   const int V = a.Cg / 8;
   const int total = a.HW * V;
+  const int beg = static_cast<int>(static_cast<long long>(total) * rank / cs);
+  const int end = static_cast<int>(static_cast<long long>(total) * (rank + 1) / cs);
   const float mean = a.stats[(n * a.groups + g) * 2], rstd = a.stats[(n * a.groups + g) * 2 + 1];
   float s1 = 0.f, s2 = 0.f;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
     const int pix = i / V;
     float dzg[8], xhat[8];
     gn_bwd_terms8(a, b, n, pix / a.W, pix % a.W, g * a.Cg + (i % V) * 8, mean, rstd, dzg, xhat);
@@ -382,24 +434,55 @@ gn_fused_bwd_kernel(const GnArgs a, const GnBwdArgs b) {
   double d0 = warp_sum_d(static_cast<double>(s1)), d1 = warp_sum_d(static_cast<double>(s2));
   if ((threadIdx.x & 31) == 0) { sh0[threadIdx.x >> 5] = d0; sh1[threadIdx.x >> 5] = d1; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double t0 = 0, t1 = 0;
+  double t0 = 0, t1 = 0;
+  if (threadIdx.x == 0)
     for (int w = 0; w < (blockDim.x >> 5); ++w) { t0 += sh0[w]; t1 += sh1[w]; }
+  gn_cluster_fold(s_part, t0, t1);
+  if (threadIdx.x == 0) {
     const double m = static_cast<double>(a.HW) * a.Cg;
     s_m1 = static_cast<float>(t0 / m);
     s_m2 = static_cast<float>(t1 / m);
   }
   __syncthreads();
   const float m1 = s_m1, m2 = s_m2;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
     const int pix = i / V;
     gn_bwd_apply_one(a, b, n, pix / a.W, pix % a.W, g * a.Cg + (i % V) * 8, mean, rstd, m1, m2);
   }
+  gn_cluster_sync();   // peers may still be reading this CTA's partials
 }
 
 // one CTA per (image, group) only pays off for tiny slices (8x8, 16x16): measured, larger slices are
 // faster with the two wide kernels (32 CTAs cannot pull enough bandwidth)
-static bool gn_use_fused(const GnArgs& a) { return static_cast<long long>(a.HW) * a.Cg <= 8192; }
+static long long gn_fused_max() {
+  static const long long v = [] {
+    const char* e = getenv("ISB_GN_FUSED_MAX");
+    return e ? atoll(e) : 8192LL;
+  }();
+  return v;
+}
+static bool gn_use_fused(const GnArgs& a) { return static_cast<long long>(a.HW) * a.Cg <= gn_fused_max(); }
+// CTAs per (image, group) for the fused kernels: enough CTAs to pull bandwidth, DSMEM fold of the partial sums
+static int gn_cluster_size_for(const GnArgs& a) {
+  const long long e = static_cast<long long>(a.HW) * a.Cg;
+  return e <= 8192 ? 1 : e <= 32768 ? 2 : e <= 65536 ? 4 : 8;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster_z(void (*kernel)(KArgs...), dim3 grid, dim3 block, int cs, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = cs;
+  cfg.attrs = attr;
+  cfg.numAttrs = cs > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 static int gn_fill_args(const isb_gn_desc* d, void* scratch, GnArgs* a) {
   ISB_CHECK_ARG(d->x1 != nullptr && d->C1 > 0, "groupnorm: x1 missing");
@@ -460,7 +543,8 @@ int isb_gn_forward(const isb_gn_desc* d, void* scratch, isb_stream_t stream) {
   cudaStream_t st = isb::as_stream(stream);
   isb::GnFwdOut o{d->y, d->y_dtype, d->raw, d->raw_dtype, d->xres};
   if (isb::gn_use_fused(a)) {
-    ISB_CUDA(isb::launch(isb::gn_fused_fwd_kernel, dim3(a.groups, a.N), 512, 0, st, a, o));
+    const int cs = isb::gn_cluster_size_for(a);
+    ISB_CUDA(isb::launch_cluster_z(isb::gn_fused_fwd_kernel, dim3(a.groups, a.N, cs), dim3(512), cs, st, a, o));
     ISB_LAUNCH_CHECK();
     return ISB_OK;
   }
@@ -484,7 +568,8 @@ int isb_gn_backward(const isb_gn_bwd_desc* d, void* scratch, isb_stream_t stream
                    d->gx2, d->acc2, d->gx2_lo, d->lo_dtype};
   cudaStream_t st = isb::as_stream(stream);
   if (isb::gn_use_fused(a)) {
-    ISB_CUDA(isb::launch(isb::gn_fused_bwd_kernel, dim3(a.groups, a.N), 512, 0, st, a, b));
+    const int cs = isb::gn_cluster_size_for(a);
+    ISB_CUDA(isb::launch_cluster_z(isb::gn_fused_bwd_kernel, dim3(a.groups, a.N, cs), dim3(512), cs, st, a, b));
     ISB_LAUNCH_CHECK();
     return ISB_OK;
   }
