@@ -91,6 +91,7 @@ typedef struct isb_conv_desc {
   int stages;
   int w_tiled;           /* 1: w is panel-tiled (see above); needs Cout % 64 == 0 */
   int two_cta;           /* 0 heuristic, 1 force the CTA-pair (cta_group::2) kernel, 2 forbid it */
+  int debug_flags;       /* profiling only (results become garbage): bit0 skip the TMA loads, bit1 skip the MMAs */
 } isb_conv_desc;
 /* Workspace (split-K partial tiles + arrival counters): must be ZERO-FILLED by the caller before its
  * first use; every launch leaves the counters at zero again, so one buffer serves all layers. */

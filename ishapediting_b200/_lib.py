@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
         ("w", c_void_p), ("bias", c_void_p), ("residual", c_void_p),
         ("out", c_void_p), ("out_dtype", c_int), ("Cout", c_int),
         ("accumulate", c_int),
-        ("block_n", c_int), ("split_k", c_int), ("stages", c_int), ("w_tiled", c_int), ("two_cta", c_int),
+        ("block_n", c_int), ("split_k", c_int), ("stages", c_int), ("w_tiled", c_int), ("two_cta", c_int), ("debug_flags", c_int),
     ]
 
 

@@ -785,7 +785,7 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   }
   const int stage_bytes = TC_A_STAGE + (p.two_cta ? bn / 2 : bn) * 128;
   const int max_stages = (TC_SMEM_LIMIT - 1024) / stage_bytes;
-  int stages = d->stages % 100;
+  int stages = d->stages;
   if (stages == 0) {
     if (p.two_cta) {
       stages = bn <= 128 ? 4 : 5;
@@ -816,7 +816,7 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   p.partial = nullptr;
   p.counters = nullptr;
   p.w_tiled = d->w_tiled;
-  p.debug = d->stages >= 100 ? d->stages / 100 : 0;   // profiling hook: stages = 100*debug + stages
+  p.debug = d->debug_flags;
   return ISB_OK;
 }
 

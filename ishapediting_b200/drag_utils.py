@@ -20,6 +20,7 @@ What differs from the reference, by design:
 from __future__ import annotations
 
 import argparse
+import os
 import copy
 from argparse import Namespace
 
@@ -220,6 +221,10 @@ class GuidedStepper:
         if dev.type == "cuda":
             self._side = th.cuda.Stream(device=dev)
             self._ev_fork, self._ev_join = th.cuda.Event(), th.cuda.Event()
+            self._side_bwd = (th.cuda.Stream(device=dev), th.cuda.Event(), th.cuda.Event())
+        self._film = {}
+        self._film_cache = os.environ.get("ISB_FILM_CACHE", "1") != "0"
+        self._bwd_branches = os.environ.get("ISB_SIDE_BWD", "1") != "0"
         self._graph = None
         self._warm = 0
 
@@ -243,6 +248,15 @@ class GuidedStepper:
     def _body(self):
         plan, ops, geo = self.plan, self.ops, self.geo
         overlap = self.overlap_tail and ops.device.type == "cuda"
+        plan.film_external = self._film_cache   # FiLM rows of this timestep were loaded into plan.film_all by step()
+        plan.side = self._side_bwd if (overlap and self._bwd_branches) else None
+        try:
+            self._body_inner(plan, ops, overlap)
+        finally:
+            plan.film_external = False
+            plan.side = None
+
+    def _body_inner(self, plan, ops, overlap):
         inter = plan.forward(self.img, plan.t_dev, self.feat_layer, upto_feat_only=overlap)
         if overlap:
             # The layers behind the intermediate feature (output_blocks[9..14] + out: 292 of the 635 forward
@@ -274,6 +288,14 @@ class GuidedStepper:
         """Advance self.img from respaced step i to i-1.  origin_feature: (3,S,S,Ca) device tensor."""
         self.coef.copy_(self.coef_table[i])
         self.plan.t_dev.copy_(self.t_table[i:i + 1].expand(self.batch))
+        film = self._film.get(i)           # the timestep-embedding path depends only on t: computed once per step index
+        if not self._film_cache:
+            pass
+        elif film is None:
+            self.plan.compute_film()
+            self._film[i] = self.plan.film_all.clone()
+        else:
+            self.plan.film_all.copy_(film)
         self.origin.copy_(origin_feature)
         if noise is None:
             self.noise.normal_()

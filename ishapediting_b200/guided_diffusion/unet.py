@@ -196,18 +196,31 @@ class _ResLayer:
         N, H, W, Cin, Ho, Wo, Co = self.dims
         g_out, g_out_lo = self.out.grad, self.out.grad_lo
         g_a2 = plan.scratch("g", (N, Ho, Wo, Co), th.float32)
+        joined = None
+        if self.has_skip_conv:
+            gres = plan.scratch("g2", (N, H, W, Cin), th.float32)
+            if plan.side is not None:
+                # the 1x1 skip backward only needs g_out: run it beside the conv2 -> GN2 -> conv1 chain
+                side, ev_fork, ev_join = plan.side
+                ev_fork.record(th.cuda.current_stream())
+                with th.cuda.stream(side):
+                    side.wait_event(ev_fork)
+                    ops.conv(g_out_lo, self.wskip_d, None, 1, gres)
+                    ev_join.record(side)
+                joined = ev_join
+            else:
+                ops.conv(g_out_lo, self.wskip_d, None, 1, gres)
+            at_input = True
+        else:
+            gres, at_input = g_out, False
         ops.conv(g_out_lo, self.w2_d, None, 3, g_a2)
         g_h1_lo = plan.scratch("glo", (N, Ho, Wo, Co), lo)
         ops.gn_backward(self.h1, None, self.g2, self.be2, plan.film_all, self.film_off, True, 0, self.stats2,
                         g_a2, None, False, None, False, g_h1_lo, None, False, None)
         g_a1 = plan.scratch("g", (N, Ho, Wo, Cin), th.float32)
         ops.conv(g_h1_lo, self.w1_d, None, 3, g_a1)
-        if self.has_skip_conv:
-            gres = plan.scratch("g2", (N, H, W, Cin), th.float32)
-            ops.conv(g_out_lo, self.wskip_d, None, 1, gres)
-            at_input = True
-        else:
-            gres, at_input = g_out, False
+        if joined is not None:
+            th.cuda.current_stream().wait_event(joined)
         s1 = self.srcs[0]
         s2 = self.srcs[1] if len(self.srcs) > 1 else None
         plan.ensure_grad(s1)
@@ -279,6 +292,8 @@ class _Plan:
         self._scratch = {}
         self.layers = []          # execution order, objects with forward()/backward()/out
         self.generation = 0
+        self.film_external = False
+        self.side = None          # (stream, fork_event, join_event) for branch-level concurrency in the backward
         lo = self.lo
         Cin = model.in_channels
         self.cin_pad = ((Cin + 63) // 64) * 64
@@ -350,6 +365,11 @@ class _Plan:
         self.out_a = self.scratch("a", (N, H, W, h.val.shape[3]), lo)
         self.out_nhwc = ops.empty((N, H, W, conv.weight.shape[0]))
 
+    def compute_film(self):
+        """film_all[n] = every ResBlock's emb_layers(time_embed(sinusoid(t_dev[n]))) — depends only on the timestep."""
+        self.ops.time_embed(self.t_dev, self.freqs, self.te_w1, self.te_b1, self.te_w2, self.te_b2, self.w_all,
+                            self.b_all, self.te_scratch, self.film_all)
+
     # -- scratch buffers shared by shape-compatible transient tensors --------------------------
     def scratch(self, tag, shape, dtype):
         n = 1
@@ -379,8 +399,8 @@ class _Plan:
             self.x_nchw.copy_(x_nchw)
         if t_orig.data_ptr() != self.t_dev.data_ptr():
             self.t_dev.copy_(t_orig)
-        ops.time_embed(self.t_dev, self.freqs, self.te_w1, self.te_b1, self.te_w2, self.te_b2, self.w_all, self.b_all,
-                       self.te_scratch, self.film_all)
+        if not self.film_external:     # GuidedStepper caches the per-timestep FiLM rows and fills film_all itself
+            self.compute_film()
         ops.to_nhwc(self.x_nchw, self.x_lo)
         ops.conv(self.x_lo, self.w_in, self.b_in, 3, self.h0.val)
         inter = self.block_out[feat_layer] if feat_layer >= 0 else None

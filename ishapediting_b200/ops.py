@@ -157,6 +157,7 @@ class CudaOps:
         if tune:
             d.block_n, d.split_k, d.stages = tune.get("block_n", 0), tune.get("split_k", 0), tune.get("stages", 0)
             d.two_cta = tune.get("two_cta", 0)
+            d.debug_flags = tune.get("debug", 0)
         ws, ws_bytes = self._workspace(self.lib.isb_conv2d_workspace(C.byref(d)))
         _lib.check(self.lib.isb_conv2d(C.byref(d), _p(ws), ws_bytes, _stream()), "isb_conv2d")
         return out
