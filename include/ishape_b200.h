@@ -271,6 +271,9 @@ int isb_triplane_decode_points(const float* planes_hwc, int R, const isb_triplan
 /* ---- introspection ---------------------------------------------------- */
 /* Number of kernels this library has launched in this process (all threads). */
 uint64_t isb_launch_count(void);
+/* Profiling only (tools/trace_conv.py): conv launches made with isb_conv_desc.debug_flags bit 2 write per-CTA
+ * %globaltimer phase stamps ([cta][16] uint64 + a per-iteration area, 4096*16*8 bytes) to this device buffer. */
+void isb_debug_set_trace(void* device_buffer);
 
 #ifdef __cplusplus
 }

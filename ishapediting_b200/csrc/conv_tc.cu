@@ -28,6 +28,7 @@ constexpr int TC_SMEM_LIMIT = 227 * 1024 - 2048;  // dynamic part; the kernel al
 
 struct TcParams {
   int tw, th, nb;
+  int tw_log2, pi_log2;   // tw and tw*th are powers of two
   int tiles_w, tiles_h, tiles_n;
   int N, H, W;
   int Cout, block_n;
@@ -45,6 +46,7 @@ struct TcParams {
   int accumulate;
   float* partial;  // != nullptr when splits > 1: [tile][split][128][block_n] fp32
   int* counters;   // [tiles] arrival counters (zero between launches)
+  unsigned long long* trace;  // profiling only (debug bit2): [cta][16] %globaltimer stamps of the pipeline phases
 };
 
 // ---- PTX wrappers ---------------------------------------------------------
@@ -73,6 +75,20 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+// profiling only: one phase stamp of this CTA (slot 15 holds the SM id)
+__device__ __forceinline__ void tc_stamp(const unsigned long long* trace_c, int slot) {
+  unsigned long long* trace = const_cast<unsigned long long*>(trace_c);
+  if (trace) {
+    const size_t cta = (static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    trace[cta * 16 + slot] = global_timer_ns();
+  }
+}
+// profiling only: per-k-iteration SM-clock stamps of CTA (0,0,0), rows of 4 behind the 3000 CTA records
+__device__ __forceinline__ void tc_stamp_iter(const unsigned long long* trace_c, int iter, int slot) {
+  unsigned long long* trace = const_cast<unsigned long long*>(trace_c);
+  if (trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && iter < 160)
+    trace[3000 * 16 + iter * 4 + slot] = static_cast<unsigned long long>(clock64());
 }
 // Bounded wait: a pipeline bug must trap (CUDA error to the caller), never hang the GPU.  The fast path is
 // a bare try_wait loop (the instruction itself suspends the thread for a HW time slice); the SM cycle
@@ -240,6 +256,142 @@ __device__ __forceinline__ void epilogue_store8(const TcParams& p, float* f, siz
   store8(p.out, off, p.out_dtype, f);
 }
 
+// Direct epilogue of one warp (32 accumulator rows = TMEM lanes 32q..32q+31).  tcgen05.ld hands every lane 32
+// consecutive channels of ITS pixel row, and rows are Cout*4 bytes apart in memory: storing from that layout
+// touches 32 different 128-byte lines per instruction (measured: 7-9 us per 128x128..256 tile, 4x the HBM time).
+// So each 32x32 chunk is transposed through a padded per-warp staging area (stride 36 floats: conflict-free for
+// both the row-wise 16-byte writes and the 4-rows-by-128-bytes reads) and leaves as full 128-byte row segments;
+// bias / residual / accumulate are applied on the coalesced side.
+constexpr int TC_STG_STRIDE = 36 * 4;                  // bytes per staged row
+constexpr int TC_STG_WARP = 32 * TC_STG_STRIDE;        // 4608 B per warp
+struct EpiDst {
+  void* out;              // row-major [rows][ld]
+  int dtype, ld;
+  const float* bias;      // indexed by destination column, or nullptr
+  const float* residual;  // same layout as out (fp32), or nullptr
+  int accumulate;
+  int col_limit;          // columns >= col_limit do not exist (multiple of 32)
+};
+// residual (+ previous out) and store 4 consecutive channels at element offset `off` (bias already added)
+__device__ __forceinline__ void epilogue_store4_nb(const EpiDst& e, float4 f, size_t off) {
+  if (e.residual != nullptr) {
+    const float4 r4 = __ldg(reinterpret_cast<const float4*>(e.residual + off));
+    f.x += r4.x; f.y += r4.y; f.z += r4.z; f.w += r4.w;
+  }
+  if (e.dtype == ISB_F32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
+    if (e.accumulate) {
+      const float4 a4 = *o;
+      f.x += a4.x; f.y += a4.y; f.z += a4.z; f.w += a4.w;
+    }
+    *o = f;
+  } else {
+    uint2 u;
+    u.x = pack_bf16x2(f.x, f.y);
+    u.y = pack_bf16x2(f.z, f.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = u;
+  }
+}
+__device__ __forceinline__ void epilogue_store4(const EpiDst& e, float4 f, size_t off, int col) {
+  if (e.bias != nullptr) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+    f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
+  }
+  epilogue_store4_nb(e, f, off);
+}
+// `row` = destination row of this lane's accumulator row, `col_base` = destination column of accumulator column 0
+__device__ __forceinline__ void epilogue_direct_warp(const EpiDst& e, int nchunks, uint32_t tmem_base, uint32_t stg,
+                                                     int q, int lane, uint32_t row, bool valid, int col_base) {
+  const int sub = lane >> 3;
+  const int cv = (lane & 7) * 4;
+  const uint32_t my_row = stg + static_cast<uint32_t>(lane) * TC_STG_STRIDE;
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  for (int c = 0; c < nchunks; ++c) {
+    const int col0 = col_base + c * 32;
+    if (col0 >= e.col_limit) break;  // warp-uniform
+    uint32_t v[32];
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + static_cast<uint32_t>(j * 16)),
+                   "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                   : "memory");
+    __syncwarp();
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + cv));
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int rsel = g * 4 + sub;
+      float4 f;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
+                   : "r"(stg + static_cast<uint32_t>(rsel * TC_STG_STRIDE + cv * 4))
+                   : "memory");
+      const uint32_t m_row = __shfl_sync(0xffffffffu, row, rsel);
+      if (!((vmask >> rsel) & 1u)) continue;
+      f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
+      epilogue_store4_nb(e, f, static_cast<size_t>(m_row) * e.ld + col0 + cv);
+    }
+    __syncwarp();
+  }
+}
+
+// Cluster split-K fold.  Every CTA of the cluster has written its fp32 partial tile (row-major [128][block_n],
+// coalesced) to the L2-resident workspace; CTA `split` owns rows [split*R, (split+1)*R) of the VALID rows of the
+// output tile and sums them over the S partials in rank order (deterministic).  All loads of a batch (16 x 16 B per
+// thread) are issued before the first add.  (The first version of this fold pulled the partials from the peers'
+// shared memory through DSMEM: the phase trace showed ~6 B/cycle/SM, 3-8 us per launch; L2 sustains 10x that.)
+template <int S>
+__device__ __forceinline__ void cluster_fold(const TcParams& p, const EpiDst& e, const float* tile_base, int split,
+                                             int et, int n0, int h0, int w0, int cout0) {
+  constexpr int U = 16 / S;
+  const int per_img = p.tw * p.th;
+  int valid_rows = (p.N - n0) * per_img;
+  if (valid_rows > TC_BLOCK_M) valid_rows = TC_BLOCK_M;
+  const int R = (valid_rows + S - 1) / S;
+  const int row0 = split * R;
+  int rows = valid_rows - row0;
+  if (rows > R) rows = R;
+  const int vec_per_row = p.block_n / 4;
+  const int nvec = rows * vec_per_row;          // <= 0 when this rank owns no valid row
+  const size_t tile_elems = static_cast<size_t>(TC_BLOCK_M) * p.block_n;
+  for (int base = et; base < nvec; base += 128 * U) {
+    float4 buf[U][S];
+    int rr[U], cc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * 128;
+      const int rl = idx / vec_per_row;
+      rr[u] = row0 + rl;
+      cc[u] = (idx - rl * vec_per_row) * 4;
+      if (idx < nvec) {
+        const float* src = tile_base + static_cast<size_t>(rr[u]) * p.block_n + cc[u];
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2) buf[u][s2] = __ldcg(reinterpret_cast<const float4*>(src + s2 * tile_elems));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * 128;
+      const int col = cout0 + cc[u];
+      if (idx >= nvec || col >= p.Cout) continue;
+      float4 f = buf[u][0];
+#pragma unroll
+      for (int s2 = 1; s2 < S; ++s2) {
+        f.x += buf[u][s2].x; f.y += buf[u][s2].y; f.z += buf[u][s2].z; f.w += buf[u][s2].w;
+      }
+      if (et == 0 && base == 0 && u == 0) tc_stamp(p.trace, 10);
+      const int rn = rr[u] >> p.pi_log2;
+      const int rrem = rr[u] & (per_img - 1);
+      const int rh = rrem >> p.tw_log2;
+      const int rw = rrem & (p.tw - 1);
+      const size_t mm = (static_cast<size_t>(n0 + rn) * p.H + (h0 + rh)) * p.W + (w0 + rw);
+      epilogue_store4(e, f, mm * p.Cout + col, col);
+    }
+  }
+}
+
 // ---- the kernel -------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
@@ -251,6 +403,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ int split_is_last;
+  if (threadIdx.x == 0) {
+    tc_stamp(p.trace, 0);
+    if (p.trace) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const size_t cta = (static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      p.trace[cta * 16 + 15] = smid;
+    }
+  }
 
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
@@ -270,6 +431,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int split = blockIdx.z;
   const int k_begin = static_cast<int>(static_cast<long long>(p.k_iters) * split / p.splits);
   const int k_end = static_cast<int>(static_cast<long long>(p.k_iters) * (split + 1) / p.splits);
+  EpiDst out_dst;
+  out_dst.out = p.out;
+  out_dst.dtype = p.out_dtype;
+  out_dst.ld = p.Cout;
+  out_dst.bias = p.bias;
+  out_dst.residual = p.residual;
+  out_dst.accumulate = p.accumulate;
+  out_dst.col_limit = p.Cout;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -295,63 +464,79 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) tc_stamp(p.trace, 1);
 
   if (warp == 0) {
     // ===== TMA producer =====
+    // One thread, latency-bound: every dependent instruction costs its full latency, so the loop carries its
+    // state (stage, phase, filter tap, channel chunk) incrementally — no integer divisions per k-iteration.
     if (lane == 0) {
       const int seg0_iters = p.ntaps * p.chunks0;
       const int niter = k_end - k_begin;
       const int npre = niter < p.stages ? niter : p.stages;
-      auto load_b = [&](int i) {
-        const int it = k_begin + i;
-        const int s = i % p.stages;
-        const uint32_t b_dst = tiles_addr + static_cast<uint32_t>(s) * stage_bytes + TC_A_STAGE;
-        int kcoord;
-        if (it < seg0_iters) {
-          const int tap = it / p.chunks0;
-          kcoord = tap * p.Cin + (it - tap * p.chunks0) * TC_BLOCK_K;
-        } else {
-          kcoord = p.ntaps * p.Cin + (it - seg0_iters) * TC_BLOCK_K;
-        }
-        if (p.w_tiled) tma_load_4d(b_dst, &mapB, smem_u32(&full_bar[s]), 0, 0, kcoord / TC_BLOCK_K, cout0 / 64);
-        else tma_load_2d(b_dst, &mapB, smem_u32(&full_bar[s]), kcoord, cout0);
-      };
-      auto load_a = [&](int i) {
-        const int it = k_begin + i;
-        const int s = i % p.stages;
-        const uint32_t a_dst = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        if (it < seg0_iters) {
-          const int tap = it / p.chunks0;
-          const int chunk = it - tap * p.chunks0;
-          int dh = 0, dw = 0;
-          if (p.ntaps == 9) {
-            dh = tap / 3 - 1;
-            dw = tap % 3 - 1;
-          }
-          tma_load_4d(a_dst, &mapA, fb, chunk * TC_BLOCK_K, w0 + dw, h0 + dh, n0);
-        } else {
-          tma_load_4d(a_dst, &mapA2, fb, (it - seg0_iters) * TC_BLOCK_K, w0, h0, n0);
-        }
-      };
+      const bool skip_tma = (p.debug & 1) != 0;
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       // The weight panels never change during a step: start streaming them into the ring before the
       // producer of our activations has even finished (PDL), then wait and fetch the activations.
-      const bool skip_tma = (p.debug & 1) != 0;
+      // (weight K coordinate of k-iteration `it` is simply it * 64 in both K segments)
       for (int i = 0; i < npre; ++i) {
-        mbar_expect_tx(smem_u32(&full_bar[i]), skip_tma ? 0u : stage_bytes);
-        if (!skip_tma) load_b(i);
+        mbar_expect_tx(full0 + 8u * i, skip_tma ? 0u : stage_bytes);
+        if (!skip_tma) {
+          const uint32_t b_dst = tiles_addr + static_cast<uint32_t>(i) * stage_bytes + TC_A_STAGE;
+          if (p.w_tiled) tma_load_4d(b_dst, &mapB, full0 + 8u * i, 0, 0, k_begin + i, cout0 / 64);
+          else tma_load_2d(b_dst, &mapB, full0 + 8u * i, (k_begin + i) * TC_BLOCK_K, cout0);
+        }
       }
       pdl_wait();
+      tc_stamp(p.trace, 2);
+      // activation-side iterator
+      int tap, chunk, dh = 0, dw = 0;
+      bool seg1 = k_begin >= seg0_iters;
+      if (seg1) {
+        tap = p.ntaps;
+        chunk = k_begin - seg0_iters;
+      } else {
+        tap = k_begin / p.chunks0;
+        chunk = k_begin - tap * p.chunks0;
+        if (p.ntaps == 9) {
+          dh = tap / 3 - 1;
+          dw = tap % 3 - 1;
+        }
+      }
+      auto load_a = [&](uint32_t a_dst, uint32_t fb) {
+        if (!seg1) tma_load_4d(a_dst, &mapA, fb, chunk * TC_BLOCK_K, w0 + dw, h0 + dh, n0);
+        else tma_load_4d(a_dst, &mapA2, fb, chunk * TC_BLOCK_K, w0, h0, n0);
+        if (++chunk == p.chunks0 && !seg1) {
+          chunk = 0;
+          if (++tap == p.ntaps) {
+            seg1 = true;
+            dh = 0;
+            dw = 0;
+          } else if (p.ntaps == 9 && ++dw == 2) {
+            dw = -1;
+            ++dh;
+          }
+        }
+      };
       if (!skip_tma)
-        for (int i = 0; i < npre; ++i) load_a(i);
+        for (int i = 0; i < npre; ++i) load_a(tiles_addr + static_cast<uint32_t>(i) * stage_bytes, full0 + 8u * i);
+      int s = npre == p.stages ? 0 : npre;
+      uint32_t ph = 0;                     // parity of the "slot free" phase being waited for
       for (int i = npre; i < niter; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = static_cast<uint32_t>(i / p.stages) & 1u;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-        mbar_expect_tx(smem_u32(&full_bar[s]), skip_tma ? 0u : stage_bytes);
+        mbar_wait(empty0 + 8u * s, ph);
+        tc_stamp_iter(p.trace, i, 0);
+        const uint32_t fb = full0 + 8u * s;
+        const uint32_t a_dst = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
+        mbar_expect_tx(fb, skip_tma ? 0u : stage_bytes);
         if (!skip_tma) {
-          load_a(i);
-          load_b(i);
+          load_a(a_dst, fb);
+          if (p.w_tiled) tma_load_4d(a_dst + TC_A_STAGE, &mapB, fb, 0, 0, k_begin + i, cout0 / 64);
+          else tma_load_2d(a_dst + TC_A_STAGE, &mapB, fb, (k_begin + i) * TC_BLOCK_K, cout0);
+        }
+        tc_stamp_iter(p.trace, i, 1);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1u;
         }
       }
     }
@@ -362,16 +547,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
                              (static_cast<uint32_t>(p.block_n >> 3) << 17) |
                              (static_cast<uint32_t>(TC_BLOCK_M >> 4) << 24);
-      for (int it = k_begin; it < k_end; ++it) {
-        const int i = it - k_begin;
-        const int s = i % p.stages;
-        const uint32_t ph = static_cast<uint32_t>(i / p.stages) & 1u;
-        mbar_wait(smem_u32(&full_bar[s]), ph);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const int niter = k_end - k_begin;
+      const bool skip_mma = (p.debug & 2) != 0;
+      int s = 0;
+      uint32_t ph = 0;
+      uint64_t adesc = make_desc_sw128(tiles_addr);
+      const uint64_t desc_step = static_cast<uint64_t>(stage_bytes >> 4);
+      const uint64_t desc_b_off = static_cast<uint64_t>(TC_A_STAGE >> 4);
+      const uint64_t adesc0 = adesc;
+      for (int i = 0; i < niter; ++i) {
+        mbar_wait(full0 + 8u * s, ph);
         tc_fence_after();
-        const uint32_t a_addr = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
-        const uint64_t adesc = make_desc_sw128(a_addr);
-        const uint64_t bdesc = make_desc_sw128(a_addr + TC_A_STAGE);
-        if (!(p.debug & 2)) {
+        if (i == 0) tc_stamp(p.trace, 3);
+        tc_stamp_iter(p.trace, i, 2);
+        if (!skip_mma) {
+          const uint64_t bdesc = adesc + desc_b_off;
 #pragma unroll
           for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
@@ -379,9 +570,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                       bdesc + static_cast<uint64_t>(k * 2), idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
         }
-        umma_commit(smem_u32(&empty_bar[s]));  // frees the smem slot when these MMAs retire
+        umma_commit(empty0 + 8u * s);  // frees the smem slot when these MMAs retire
+        tc_stamp_iter(p.trace, i, 3);
+        adesc += desc_step;
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1u;
+          adesc = adesc0;
+        }
       }
       umma_commit(smem_u32(&tmem_full_bar));   // accumulator complete
+      tc_stamp(p.trace, 4);
     }
   } else {
     // ===== epilogue warps 2..5 =====
@@ -399,27 +598,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tc_fence_after();
+    if (threadIdx.x == 64) tc_stamp(p.trace, 5);
     pdl_wait();   // residual / accumulate reads and every global write come after the predecessor
 
     bool do_final = true;
     const size_t tile_id = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
     if (p.cluster) {
-      // Cluster split-K: park the fp32 partial tile in this CTA's own shared memory (the pipeline
-      // buffers are free: every MMA that read them has retired); the fold happens after the cluster
-      // barrier below, through distributed shared memory.
+      // Cluster split-K: park the fp32 partial tile in the workspace (stays in L2); the fold happens after the
+      // cluster barrier below.
       do_final = false;
-      const uint32_t row_addr = tiles_addr + static_cast<uint32_t>(r) * static_cast<uint32_t>(p.block_n + 4) * 4u;
-      for (int c = 0; c < nchunks; ++c) {
-        if (cout0 + c * 32 >= p.Cout) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + static_cast<uint32_t>(c * 128 + j * 16)),
-                       "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                       : "memory");
-      }
+      EpiDst pe;
+      pe.out = p.partial + (tile_id * p.splits + split) * static_cast<size_t>(TC_BLOCK_M) * p.block_n;
+      pe.dtype = ISB_F32;
+      pe.ld = p.block_n;
+      pe.bias = nullptr;
+      pe.residual = nullptr;
+      pe.accumulate = 0;
+      pe.col_limit = p.Cout - cout0 < p.block_n ? p.Cout - cout0 : p.block_n;
+      epilogue_direct_warp(pe, nchunks, tmem_base, tiles_addr + static_cast<uint32_t>(q) * TC_STG_WARP, q, lane,
+                           static_cast<uint32_t>(r), valid, 0);
     } else if (p.splits > 1) {
       // Split-K: every CTA parks its fp32 partial tile in the workspace; the LAST CTA to arrive for this
       // output tile folds all partials in split order (deterministic) and runs the real epilogue.
@@ -449,22 +646,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 
     if (do_final && p.splits == 1) {
-      for (int c = 0; c < nchunks; ++c) {
-        const int col0 = cout0 + c * 32;
-        if (col0 >= p.Cout) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
-        tmem_ld_wait();
-        if (!valid) continue;
-        const size_t off = m * p.Cout + col0;
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
-          epilogue_store8(p, f, off + j8 * 8, col0 + j8 * 8);
-        }
-      }
+      epilogue_direct_warp(out_dst, nchunks, tmem_base, tiles_addr + static_cast<uint32_t>(q) * TC_STG_WARP, q, lane,
+                           static_cast<uint32_t>(m), valid, cout0);
     } else if (do_final) {
       // fold: the 128 epilogue threads sweep the tile as a flat array (coalesced 32 B per thread),
       // summing the partials in split order
@@ -497,38 +680,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   }
 
+  if (threadIdx.x == 64) tc_stamp(p.trace, 6);
   if (p.cluster) {
     cluster_sync_all();   // every CTA of the cluster has parked its partial tile
+    if (threadIdx.x == 64) tc_stamp(p.trace, 7);
     if (warp >= 2) {
-      // CTA `split` folds rows [split*R, (split+1)*R) of the tile over all ranks, in rank order
       const int et = threadIdx.x - 64;
-      const int R = TC_BLOCK_M / p.splits;
-      const int vec_per_row = p.block_n / 8;
-      const int nvec = R * vec_per_row;
-      const int per_img = p.tw * p.th;
-      for (int idx = et; idx < nvec; idx += 128) {
-        const int rr = split * R + idx / vec_per_row;
-        const int cc = (idx % vec_per_row) * 8;
-        const int col = cout0 + cc;
-        const int rn = rr / per_img;
-        const int rrem = rr - rn * per_img;
-        const int rh = rrem / p.tw;
-        const int rw = rrem - rh * p.tw;
-        if (n0 + rn >= p.N || col >= p.Cout) continue;
-        const uint32_t laddr = tiles_addr + (static_cast<uint32_t>(rr) * static_cast<uint32_t>(p.block_n + 4) +
-                                             static_cast<uint32_t>(cc)) * 4u;
-        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int s2 = 0; s2 < p.splits; ++s2) {
-          const float4 u0 = ld_dsmem_f4(laddr, static_cast<uint32_t>(s2));
-          const float4 u1 = ld_dsmem_f4(laddr + 16u, static_cast<uint32_t>(s2));
-          f[0] += u0.x; f[1] += u0.y; f[2] += u0.z; f[3] += u0.w;
-          f[4] += u1.x; f[5] += u1.y; f[6] += u1.z; f[7] += u1.w;
-        }
-        const size_t mm = (static_cast<size_t>(n0 + rn) * p.H + (h0 + rh)) * p.W + (w0 + rw);
-        epilogue_store8(p, f, mm * p.Cout + col, col);
-      }
+      const size_t tile_id = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
+      const float* tile_base = p.partial + tile_id * p.splits * static_cast<size_t>(TC_BLOCK_M) * p.block_n;
+      if (p.splits == 2) cluster_fold<2>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0);
+      else if (p.splits == 4) cluster_fold<4>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0);
+      else cluster_fold<8>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0);
     }
-    cluster_sync_all();   // nobody leaves (and frees its shared memory) while peers still read it
+    if (threadIdx.x == 64) tc_stamp(p.trace, 8);
   }
 
   tc_fence_before();
@@ -538,6 +702,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                  "r"(static_cast<uint32_t>(p.tmem_cols))
                  : "memory");
   }
+  if (threadIdx.x == 64) tc_stamp(p.trace, 9);
 }
 
 // ---- CTA-pair kernel: two SMs of one TPC cooperate on a 256 x block_n output tile ---------------
@@ -572,7 +737,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const int tile_n = mt / p.tiles_h;
   const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.nb;
   const int cout0 = blockIdx.y * p.block_n;
+  EpiDst out_dst;
+  out_dst.out = p.out;
+  out_dst.dtype = p.out_dtype;
+  out_dst.ld = p.Cout;
+  out_dst.bias = p.bias;
+  out_dst.residual = p.residual;
+  out_dst.accumulate = p.accumulate;
+  out_dst.col_limit = p.Cout;
   const int niter = p.k_iters;
+  if (threadIdx.x == 0) {
+    tc_stamp(p.trace, 0);
+    if (p.trace) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const size_t cta = (static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      p.trace[cta * 16 + 15] = smid;
+    }
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -597,36 +779,57 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   cluster_sync_all();     // barriers of both CTAs initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) tc_stamp(p.trace, 1);
 
   if (warp == 0) {
-    // ===== TMA producer (both CTAs) =====
+    // ===== TMA producer (both CTAs) =====  (incremental loop state, see conv_tc_kernel)
     if (lane == 0) {
-      const int seg0_iters = p.ntaps * p.chunks0;
+      const int npre = niter < p.stages ? niter : p.stages;
+      const uint32_t full0 = mapa_u32(smem_u32(&full_bar[0]), 0);     // the LEADER's "full" barriers
+      const uint32_t full0_local = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const int brow = cout0 + static_cast<int>(rank) * half_n;
+      // weights first (they do not depend on the predecessor kernel), activations after the PDL wait
+      for (int i = 0; i < npre; ++i) {
+        if (leader) mbar_expect_tx(full0_local + 8u * i, 2u * stage_bytes);
+        else mbar_arrive_cluster(full0 + 8u * i);
+        tma2_load_2d(tiles_addr + static_cast<uint32_t>(i) * stage_bytes + TC_A_STAGE, &mapB, full0 + 8u * i,
+                     i * TC_BLOCK_K, brow);
+      }
       pdl_wait();
-      for (int i = 0; i < niter; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = static_cast<uint32_t>(i / p.stages) & 1u;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-        const uint32_t fb_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
-        if (leader) mbar_expect_tx(smem_u32(&full_bar[s]), 2u * stage_bytes);
-        else mbar_arrive_cluster(fb_leader);
-        const uint32_t a_dst = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
-        const uint32_t b_dst = a_dst + TC_A_STAGE;
-        const int brow = cout0 + static_cast<int>(rank) * half_n;
-        if (i < seg0_iters) {
-          const int tap = i / p.chunks0;
-          const int chunk = i - tap * p.chunks0;
-          int dh = 0, dw = 0;
-          if (p.ntaps == 9) {
-            dh = tap / 3 - 1;
-            dw = tap % 3 - 1;
+      tc_stamp(p.trace, 2);
+      int tap = 0, chunk = 0, dh = p.ntaps == 9 ? -1 : 0, dw = dh;
+      bool seg1 = p.ntaps * p.chunks0 == 0;
+      auto load_a = [&](uint32_t a_dst, uint32_t fb) {
+        if (!seg1) tma2_load_4d(a_dst, &mapA, fb, chunk * TC_BLOCK_K, w0 + dw, h0 + dh, n0);
+        else tma2_load_4d(a_dst, &mapA2, fb, chunk * TC_BLOCK_K, w0, h0, n0);
+        if (++chunk == p.chunks0 && !seg1) {
+          chunk = 0;
+          if (++tap == p.ntaps) {
+            seg1 = true;
+            dh = 0;
+            dw = 0;
+          } else if (p.ntaps == 9 && ++dw == 2) {
+            dw = -1;
+            ++dh;
           }
-          tma2_load_4d(a_dst, &mapA, fb_leader, chunk * TC_BLOCK_K, w0 + dw, h0 + dh, n0);
-          tma2_load_2d(b_dst, &mapB, fb_leader, tap * p.Cin + chunk * TC_BLOCK_K, brow);
-        } else {
-          const int chunk = i - seg0_iters;
-          tma2_load_4d(a_dst, &mapA2, fb_leader, chunk * TC_BLOCK_K, w0, h0, n0);
-          tma2_load_2d(b_dst, &mapB, fb_leader, p.ntaps * p.Cin + chunk * TC_BLOCK_K, brow);
+        }
+      };
+      for (int i = 0; i < npre; ++i) load_a(tiles_addr + static_cast<uint32_t>(i) * stage_bytes, full0 + 8u * i);
+      int s = npre == p.stages ? 0 : npre;
+      uint32_t ph = 0;
+      for (int i = npre; i < niter; ++i) {
+        mbar_wait(empty0 + 8u * s, ph);
+        tc_stamp_iter(p.trace, i, 0);
+        const uint32_t fb = full0 + 8u * s;
+        if (leader) mbar_expect_tx(full0_local + 8u * s, 2u * stage_bytes);
+        else mbar_arrive_cluster(fb);
+        const uint32_t a_dst = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
+        load_a(a_dst, fb);
+        tma2_load_2d(a_dst + TC_A_STAGE, &mapB, fb, i * TC_BLOCK_K, brow);
+        tc_stamp_iter(p.trace, i, 1);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1u;
         }
       }
     }
@@ -636,21 +839,34 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
                              (static_cast<uint32_t>(p.block_n >> 3) << 17) |
                              (static_cast<uint32_t>(256 >> 4) << 24);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      int s = 0;
+      uint32_t ph = 0;
+      const uint64_t adesc0 = make_desc_sw128(tiles_addr);
+      uint64_t adesc = adesc0;
+      const uint64_t desc_step = static_cast<uint64_t>(stage_bytes >> 4);
+      const uint64_t desc_b_off = static_cast<uint64_t>(TC_A_STAGE >> 4);
       for (int i = 0; i < niter; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = static_cast<uint32_t>(i / p.stages) & 1u;
-        mbar_wait(smem_u32(&full_bar[s]), ph);
+        mbar_wait(full0 + 8u * s, ph);
         tc_fence_after();
-        const uint32_t a_addr = tiles_addr + static_cast<uint32_t>(s) * stage_bytes;
-        const uint64_t adesc = make_desc_sw128(a_addr);
-        const uint64_t bdesc = make_desc_sw128(a_addr + TC_A_STAGE);
+        if (i == 0) tc_stamp(p.trace, 3);
+        tc_stamp_iter(p.trace, i, 2);
+        const uint64_t bdesc = adesc + desc_b_off;
 #pragma unroll
         for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
           umma2_bf16(tmem_base, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
                      (i > 0 || k > 0) ? 1u : 0u);
-        umma2_commit_pair(smem_u32(&empty_bar[s]));
+        umma2_commit_pair(empty0 + 8u * s);
+        tc_stamp_iter(p.trace, i, 3);
+        adesc += desc_step;
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1u;
+          adesc = adesc0;
+        }
       }
       umma2_commit_pair(smem_u32(&tmem_full_bar));
+      tc_stamp(p.trace, 4);
     }
   } else {
     // ===== epilogue warps 2..5 (both CTAs, each its own 128 rows) =====
@@ -664,28 +880,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int n = n0 + pn;
     const bool valid = n < p.N;
     const size_t m = (static_cast<size_t>(n) * p.H + (h0 + ph_)) * p.W + (w0 + pw_);
-    const int nchunks = p.block_n / 32;
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tc_fence_after();
+    if (threadIdx.x == 64) tc_stamp(p.trace, 5);
     pdl_wait();
-    for (int c = 0; c < nchunks; ++c) {
-      const int col0 = cout0 + c * 32;
-      if (col0 >= p.Cout) break;
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
-      tmem_ld_wait();
-      if (!valid) continue;
-      const size_t off = m * p.Cout + col0;
-#pragma unroll
-      for (int j8 = 0; j8 < 4; ++j8) {
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
-        epilogue_store8(p, f, off + j8 * 8, col0 + j8 * 8);
-      }
-    }
+    epilogue_direct_warp(out_dst, p.block_n / 32, tmem_base, tiles_addr + static_cast<uint32_t>(q) * TC_STG_WARP, q,
+                         lane, static_cast<uint32_t>(m), valid, cout0);
   }
 
+  if (threadIdx.x == 64) tc_stamp(p.trace, 6);
   tc_fence_before();
   cluster_sync_all();     // the pair's TMEM is released together; nobody exits while the peer still needs its smem
   if (warp == 2) {
@@ -693,9 +896,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                  "r"(static_cast<uint32_t>(p.tmem_cols))
                  : "memory");
   }
+  if (threadIdx.x == 64) tc_stamp(p.trace, 9);
 }
 
 // ---- host side --------------------------------------------------------------
+static void* g_trace = nullptr;   // profiling only: phase stamps of launches made with debug bit 2
+void conv_tc_set_trace(void* ptr) { g_trace = ptr; }
+
 struct TcPlan {
   TcParams p;
   int smem_bytes;
@@ -728,6 +935,8 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   }
   ISB_CHECK_ARG(d->H % p.th == 0, "conv_tc: H=%d not divisible by tile height %d", d->H, p.th);
   p.nb = 128 / (p.tw * p.th);
+  p.tw_log2 = 31 - __builtin_clz(p.tw);
+  p.pi_log2 = 31 - __builtin_clz(p.tw * p.th);
   p.tiles_w = d->W / p.tw;
   p.tiles_h = d->H / p.th;
   p.tiles_n = cdiv(d->N, p.nb);
@@ -802,11 +1011,11 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   ISB_CHECK_ARG(stages >= 2, "conv_tc: not enough shared memory for 2 stages");
   p.stages = stages;
   plan->smem_bytes = stages * stage_bytes;
-  const int dump_bytes = TC_BLOCK_M * (bn + 4) * 4;   // cluster mode parks the fp32 tile in smem
-  if (p.cluster && plan->smem_bytes < dump_bytes) plan->smem_bytes = dump_bytes;
   plan->smem_bytes += 1024;
   plan->counter_bytes = (static_cast<size_t>(mtiles) * ntiles * sizeof(int) + 255) & ~static_cast<size_t>(255);
-  plan->ws_bytes = (splits > 1 && !p.cluster) ? plan->counter_bytes + static_cast<size_t>(mtiles) * ntiles * splits * TC_BLOCK_M * bn * sizeof(float) : 0;
+  // split-K partial tiles [tile][split][128][bn] fp32 behind the arrival counters (the cluster path does not use
+  // the counters); re-written by every launch, so they live in L2
+  plan->ws_bytes = splits > 1 ? plan->counter_bytes + static_cast<size_t>(mtiles) * ntiles * splits * TC_BLOCK_M * bn * sizeof(float) : 0;
   plan->grid = dim3(mtiles, ntiles, splits);
   p.bias = d->bias;
   p.residual = d->residual;
@@ -817,6 +1026,7 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   p.counters = nullptr;
   p.w_tiled = d->w_tiled;
   p.debug = d->debug_flags;
+  p.trace = nullptr;
   return ISB_OK;
 }
 
@@ -896,7 +1106,7 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
                     (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
                 "conv_tc: pointers must be 16-byte aligned");
   TcParams& p = plan.p;
-  if (p.splits > 1 && !p.cluster) {
+  if (p.splits > 1) {
     if (ws == nullptr || ws_bytes < plan.ws_bytes) {
       set_error("conv_tc: workspace %zu bytes < required %zu", ws_bytes, plan.ws_bytes);
       return ISB_ERR_WORKSPACE;
@@ -904,6 +1114,7 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
     p.counters = static_cast<int*>(ws);
     p.partial = reinterpret_cast<float*>(static_cast<char*>(ws) + plan.counter_bytes);
   }
+  if (p.debug & 4) p.trace = static_cast<unsigned long long*>(g_trace);   // profiling: isb_debug_set_trace()
   CUtensorMap mapA, mapA2, mapB;
   rc = encode_act_map(&mapA, d->a, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.nb);
   if (rc) return rc;

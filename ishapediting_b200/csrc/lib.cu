@@ -37,6 +37,7 @@ int num_sms() { return g_num_sms; }
 tensormap_encode_fn get_tensormap_encode() { return g_encode; }
 
 int conv_tc_init();     // conv_tc.cu: raise dynamic smem limit
+void conv_tc_set_trace(void* ptr);
 int decode_init();      // decode.cu
 
 }  // namespace isb
@@ -48,6 +49,8 @@ int isb_abi_version(void) { return ISB_ABI_VERSION; }
 const char* isb_last_error(void) { return isb::t_err; }
 
 uint64_t isb_launch_count(void) { return isb::g_launches.load(); }
+
+void isb_debug_set_trace(void* device_buffer) { isb::conv_tc_set_trace(device_buffer); }
 
 int isb_init(int device) {
   std::lock_guard<std::mutex> lk(isb::g_mu);

@@ -264,7 +264,7 @@ class GuidedStepper:
             # of small, latency-bound kernels.  Run the two concurrently and join before the update.
             main = th.cuda.current_stream()
             self._ev_fork.record(main)
-            with th.cuda.stream(self._side):
+            with th.cuda.stream(self._side), ops.workspace_slot(1):
                 self._side.wait_event(self._ev_fork)
                 plan.forward_tail()
                 self._ev_join.record(self._side)

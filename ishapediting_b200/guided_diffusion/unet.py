@@ -203,7 +203,7 @@ class _ResLayer:
                 # the 1x1 skip backward only needs g_out: run it beside the conv2 -> GN2 -> conv1 chain
                 side, ev_fork, ev_join = plan.side
                 ev_fork.record(th.cuda.current_stream())
-                with th.cuda.stream(side):
+                with th.cuda.stream(side), ops.workspace_slot(2):
                     side.wait_event(ev_fork)
                     ops.conv(g_out_lo, self.wskip_d, None, 1, gres)
                     ev_join.record(side)

@@ -7,6 +7,7 @@ imported from here.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 
@@ -57,7 +58,8 @@ class CudaOps:
         self.lo = torch.bfloat16 if mode == "bf16" else torch.float32
         self.lib = _lib.init(self.device.index or 0)
         self.tile_weights = os.environ.get("ISB_TILED_WEIGHTS", "0") == "1"
-        self._ws = None
+        self._ws = {}
+        self._ws_slot = 0
         self._gn_scratch = {}
 
     # ---- memory -----------------------------------------------------------
@@ -68,14 +70,29 @@ class CudaOps:
         return torch.zeros(shape, dtype=dtype, device=self.device)
 
     def _workspace(self, nbytes):
+        """Split-K partial tiles of the conv kernel.  One buffer per concurrency SLOT (see workspace_slot): the
+        guided step runs convolutions on up to three streams at once (forward tail, ResBlock skip dgrad), and a
+        launch owns its workspace from its first partial store to its last fold load."""
         if nbytes == 0:
             return None, 0
-        if self._ws is None or self._ws.numel() < nbytes:
+        key = self._ws_slot
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
             if torch.cuda.is_current_stream_capturing():
                 raise _lib.IsbError("conv workspace must be sized by an eager warm-up before graph capture")
             # zero-filled: the split-K arrival counters at its head must start (and are left) at 0
-            self._ws = torch.zeros(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
-        return self._ws, self._ws.numel()
+            ws = torch.zeros(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws, ws.numel()
+
+    @contextlib.contextmanager
+    def workspace_slot(self, slot):
+        """Launches made inside this context (on a side stream) use their own conv workspace."""
+        prev, self._ws_slot = self._ws_slot, slot
+        try:
+            yield
+        finally:
+            self._ws_slot = prev
 
     def _scratch(self, N, groups=32, which="fwd"):
         """GroupNorm reduction scratch (arrival counters + partials).  Forward and backward kernels get
@@ -158,6 +175,8 @@ class CudaOps:
             d.block_n, d.split_k, d.stages = tune.get("block_n", 0), tune.get("split_k", 0), tune.get("stages", 0)
             d.two_cta = tune.get("two_cta", 0)
             d.debug_flags = tune.get("debug", 0)
+        if tune and tune.get("trace") is not None:      # profiling: debug bit 2 -> phase stamps land in this tensor
+            self.lib.isb_debug_set_trace(_p(tune["trace"]))
         ws, ws_bytes = self._workspace(self.lib.isb_conv2d_workspace(C.byref(d)))
         _lib.check(self.lib.isb_conv2d(C.byref(d), _p(ws), ws_bytes, _stream()), "isb_conv2d")
         return out

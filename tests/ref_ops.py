@@ -6,6 +6,7 @@ backward ops) independently of the CUDA kernels.  Two uses:
   * on the GPU box: per-op reference the CUDA kernels are compared with.
 `mode="bf16"` emulates the tensor-core path's operand rounding (bf16 operands, fp32 accumulate).
 """
+import contextlib
 import math
 
 import torch
@@ -22,6 +23,10 @@ def _nhwc(x):
 
 class RefOps:
     name = "ref"
+
+    @contextlib.contextmanager
+    def workspace_slot(self, slot):
+        yield
 
     def __init__(self, mode="fp32", device="cpu"):
         self.mode = mode
