@@ -947,22 +947,31 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   p.chunks1 = d->a2 ? d->Cin2 / 64 : 0;
   p.k_iters = p.ntaps * p.chunks0 + p.chunks1;
   const int mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  // N tile / split-K / pipeline depth, from the cold-weight sweep in profiles/r01_conv_tune_sweep_v1.txt:
-  //  * a launch costs ~6-8 us of fixed latency (prologue, first TMA, epilogue, cluster barriers), so the
-  //    aim is enough CTAs to overlap those phases — about two per SM — not "one wave";
-  //  * split-K (cluster of 2/4/8 CTAs per output tile, DSMEM fold) as long as every CTA keeps >= 3
-  //    k-iterations; 1x1 / linear layers (short K) prefer 64-wide N tiles, 3x3 layers 128-wide.
+  // N tile / split-K / pipeline depth, from the cold-weight sweeps (profiles/r01_conv_tune_sweep_v4.txt):
+  //  * a launch has ~2 us of start latency and 3-6 us of epilogue, so the aim is enough CTAs to overlap those
+  //    phases — up to two per SM — not "one wave";
+  //  * split-K (cluster of 2/4/8 CTAs per output tile, partials folded through L2).  Layers with few output tiles
+  //    split as long as every CTA keeps >= 2 k-iterations; layers that already have >= 48 tiles only while the
+  //    CTAs keep >= 8 (the fold costs more than the iterations it saves);
+  //  * shared memory per CTA stays <= 96 KB, so that the CTAs of the NEXT launch can become resident while this
+  //    launch drains (programmatic dependent launch): their prologue and weight prefetch overlap our epilogue.
+  //    Deeper pipelines (6 stages, 144-192 KB) measured up to 2x slower in a chain of launches for that reason.
   const int sms = num_sms();
   auto splits_for = [&](int tiles) {
     int sp = 1;
-    while (sp < 8 && static_cast<long long>(tiles) * sp * 2 <= 2LL * sms && p.k_iters / (sp * 2) >= 3) sp *= 2;
+    const int need = tiles >= 48 ? 8 : 2;
+    while (sp < 8) {
+      const int next = sp * 2;
+      if (static_cast<long long>(tiles) * next > 2LL * sms || p.k_iters / next < need) break;
+      sp = next;
+    }
     return sp;
   };
   int bn = d->block_n;
   if (bn == 0) {
     if (d->Cout < 128) bn = d->Cout;                                  // 32,64,96
     else if (d->Cout % 128 != 0 && d->Cout <= 256) bn = d->Cout;      // e.g. 192: one exact tile
-    else bn = (d->ksize == 1 && d->Cout % 64 == 0) ? 64 : 128;
+    else bn = ((d->ksize == 1 || mtiles <= 2) && d->Cout % 64 == 0) ? 64 : 128;   // 1x1 / tiny images: 64-wide
   }
   ISB_CHECK_ARG(bn >= 32 && bn <= 256 && bn % 32 == 0, "conv_tc: block_n=%d must be a multiple of 32 in [32,256]", bn);
   p.block_n = bn;
@@ -998,12 +1007,10 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   if (stages == 0) {
     if (p.two_cta) {
       stages = bn <= 128 ? 4 : 5;
-    } else if (static_cast<long long>(tiles) * splits <= sms) {
-      stages = 6;                                   // alone on its SM: prefetch as deep as smem allows
+    } else {
+      stages = bn <= 64 ? 4 : bn <= 128 ? 3 : 4;    // <= 96 KB (see above); 256-wide tiles cannot, they get 4
       const int per_cta = cdiv(p.k_iters, splits);
       if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
-    } else {
-      stages = bn <= 128 ? 3 : 4;                   // leave room for a second resident CTA
     }
   }
   if (stages > max_stages) stages = max_stages;
