@@ -168,6 +168,16 @@ int isb_attention_backward(const float* qkv, const float* probs,
                            float* tmp, void* d_qkv, int lo_dtype,
                            isb_stream_t stream);
 
+/* Fused (flash) form of the same attention for the bf16 mode, 64 channels per head: the [heads,T,T]
+ * probabilities are never written.  qkv, out, d_out, d_qkv are bf16 with the layouts above; the forward keeps
+ * only lse [N,heads,T] fp32 (row log-sum-exp of the scaled scores, log2 domain); the backward recomputes P from
+ * it, writes delta [N,heads,T] = rowsum(d_out o out) as scratch and d_qkv.  T % 64 == 0, ch == 64. */
+int isb_attention_flash_forward(const void* qkv, int N, int T, int heads, int ch,
+                                void* out, float* lse, isb_stream_t stream);
+int isb_attention_flash_backward(const void* qkv, const void* out, const void* d_out,
+                                 const float* lse, int N, int T, int heads, int ch,
+                                 float* delta, void* d_qkv, isb_stream_t stream);
+
 /* ---- timestep embedding path (nn.py:102-120, unet.py:471-475,199-205) --- */
 /* film_all[n, :] = W_all @ silu(W2 @ silu(W1 @ sinus(t[n]) + b1) + b2) + b_all
  * where W_all/b_all is the row-concatenation of every ResBlock's emb_layers

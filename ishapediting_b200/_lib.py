@@ -112,6 +112,9 @@ PROTOTYPES = {
     "isb_gn_forward": (c_int, [C.POINTER(GnDesc), c_void_p, c_void_p]),
     "isb_gn_backward": (c_int, [C.POINTER(GnBwdDesc), c_void_p, c_void_p]),
     "isb_attention_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "isb_attention_flash_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "isb_attention_flash_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                             c_void_p, c_void_p, c_void_p]),
     "isb_attention_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_int, c_void_p]),
     "isb_time_embed": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

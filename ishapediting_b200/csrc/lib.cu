@@ -39,6 +39,7 @@ tensormap_encode_fn get_tensormap_encode() { return g_encode; }
 int conv_tc_init();     // conv_tc.cu: raise dynamic smem limit
 void conv_tc_set_trace(void* ptr);
 int decode_init();      // decode.cu
+int attention_flash_init();   // attention_flash.cu
 
 }  // namespace isb
 
@@ -76,6 +77,8 @@ int isb_init(int device) {
   int rc = isb::conv_tc_init();
   if (rc) return rc;
   rc = isb::decode_init();
+  if (rc) return rc;
+  rc = isb::attention_flash_init();
   if (rc) return rc;
   isb::g_init.store(true);
   return ISB_OK;

@@ -252,9 +252,16 @@ class _AttnLayer:
         T = H * W
         self.stats = ops.empty((N, 32, 2))
         self.a = plan.scratch("a", (N, H, W, Cc), lo)
-        self.qkv = ops.empty((N, H, W, 3 * Cc))
-        self.probs = ops.empty((N, self.heads, T, T))
-        self.o = plan.scratch("o", (N, H, W, Cc), lo)
+        # bf16 mode with 64-channel heads: fused attention, the [heads,T,T] probabilities are never materialised
+        self.flash = lo == th.bfloat16 and Cc // self.heads == 64 and T % 64 == 0
+        if self.flash:
+            self.qkv = ops.empty((N, H, W, 3 * Cc), lo)
+            self.lse = ops.empty((N, self.heads, T))
+            self.o = ops.empty((N, H, W, Cc), lo) if plan.want_backward else plan.scratch("o", (N, H, W, Cc), lo)
+        else:
+            self.qkv = ops.empty((N, H, W, 3 * Cc))
+            self.probs = ops.empty((N, self.heads, T, T))
+            self.o = plan.scratch("o", (N, H, W, Cc), lo)
         self.out = _T(ops.empty((N, H, W, Cc)), name)
         self.dims = (N, H, W, Cc, T)
 
@@ -262,17 +269,26 @@ class _AttnLayer:
         ops, x = self.plan.ops, self.src.val
         ops.gn_forward(x, None, self.g, self.be, None, 0, False, 0, self.stats, self.a)
         ops.conv(self.a, self.wqkv, self.bqkv, 1, self.qkv)
-        ops.attention_forward(self.qkv, self.heads, self.probs, self.o)
+        if self.flash:
+            ops.attention_flash_forward(self.qkv, self.heads, self.o, self.lse)
+        else:
+            ops.attention_forward(self.qkv, self.heads, self.probs, self.o)
         ops.conv(self.o, self.wproj, self.bproj, 1, self.out.val, residual=x)
 
     def backward(self):
         plan, ops, lo = self.plan, self.plan.ops, self.plan.lo
         N, H, W, Cc, T = self.dims
-        g_o = plan.scratch("g", (N, H, W, Cc), th.float32)
-        ops.conv(self.out.grad_lo, self.wproj_d, None, 1, g_o)
-        tmp = plan.scratch("ptmp", (N, self.heads, T, T), th.float32)
         g_qkv = plan.scratch("glo", (N, H, W, 3 * Cc), lo)
-        ops.attention_backward(self.qkv, self.probs, g_o, self.heads, tmp, g_qkv)
+        if self.flash:
+            g_o = plan.scratch("golo", (N, H, W, Cc), lo)
+            ops.conv(self.out.grad_lo, self.wproj_d, None, 1, g_o)
+            delta = plan.scratch("fadelta", (N, self.heads, T), th.float32)
+            ops.attention_flash_backward(self.qkv, self.o, g_o, self.lse, self.heads, delta, g_qkv)
+        else:
+            g_o = plan.scratch("g", (N, H, W, Cc), th.float32)
+            ops.conv(self.out.grad_lo, self.wproj_d, None, 1, g_o)
+            tmp = plan.scratch("ptmp", (N, self.heads, T, T), th.float32)
+            ops.attention_backward(self.qkv, self.probs, g_o, self.heads, tmp, g_qkv)
         g_a = plan.scratch("g", (N, H, W, Cc), th.float32)
         ops.conv(g_qkv, self.wqkv_d, None, 1, g_a)
         s = self.src

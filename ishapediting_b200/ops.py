@@ -251,6 +251,26 @@ class CudaOps:
                                                    _DT[d_qkv.dtype], _stream()), "isb_attention_backward")
         return d_qkv
 
+    def attention_flash_forward(self, qkv, heads, out, lse):
+        """Fused attention (bf16 mode, 64 channels per head): qkv [N,H,W,3C] bf16 -> out [N,H,W,C] bf16, lse [N,heads,T]."""
+        _chk(qkv, torch.bfloat16); _chk(out, torch.bfloat16); _chk(lse, torch.float32)
+        N, H, W, C3 = qkv.shape
+        T, ch = H * W, C3 // (3 * heads)
+        _lib.check(self.lib.isb_attention_flash_forward(_p(qkv), N, T, heads, ch, _p(out), _p(lse), _stream()),
+                   "isb_attention_flash_forward")
+        return out
+
+    def attention_flash_backward(self, qkv, out, d_out, lse, heads, delta, d_qkv):
+        for x in (qkv, out, d_out, d_qkv):
+            _chk(x, torch.bfloat16)
+        _chk(lse, torch.float32); _chk(delta, torch.float32)
+        N, H, W, C3 = qkv.shape
+        T, ch = H * W, C3 // (3 * heads)
+        _lib.check(self.lib.isb_attention_flash_backward(_p(qkv), _p(out), _p(d_out), _p(lse), N, T, heads, ch,
+                                                         _p(delta), _p(d_qkv), _stream()),
+                   "isb_attention_flash_backward")
+        return d_qkv
+
     # ---- timestep embedding ---------------------------------------------------------
     def time_embed(self, t, freqs, w1, b1, w2, b2, w_all, b_all, scratch, film_all):
         _chk(t, torch.int64)

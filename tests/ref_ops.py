@@ -164,6 +164,30 @@ class RefOps:
         d_qkv.copy_(g.to(d_qkv.dtype))
         return d_qkv
 
+    def attention_flash_forward(self, qkv, heads, out, lse):
+        N, H, W, C3 = qkv.shape
+        T, ch = H * W, C3 // (3 * heads)
+        x = qkv.float().reshape(N, T, heads, 3, ch)
+        q, k, v = x[:, :, :, 0], x[:, :, :, 1], x[:, :, :, 2]
+        s = torch.einsum("nthc,nshc->nhts", q, k) / math.sqrt(ch)
+        lse.copy_(torch.logsumexp(s, dim=-1) / math.log(2.0))
+        o = torch.einsum("nhts,nshc->nthc", torch.softmax(s, dim=-1), v)
+        out.copy_(o.reshape(N, H, W, heads * ch).to(out.dtype))
+        return out
+
+    def attention_flash_backward(self, qkv, out, d_out, lse, heads, delta, d_qkv):
+        N, H, W, C3 = qkv.shape
+        T, ch = H * W, C3 // (3 * heads)
+        x = qkv.detach().float().clone().requires_grad_(True)
+        with torch.enable_grad():
+            y = x.reshape(N, T, heads, 3, ch)
+            s = torch.einsum("nthc,nshc->nhts", y[:, :, :, 0], y[:, :, :, 1]) / math.sqrt(ch)
+            o = torch.einsum("nhts,nshc->nthc", torch.softmax(s, dim=-1), y[:, :, :, 2]).reshape(N, H, W, heads * ch)
+            (g,) = torch.autograd.grad((o * d_out.float()).sum(), x)
+        delta.copy_((d_out.float() * out.float()).reshape(N, T, heads, ch).sum(-1).permute(0, 2, 1))
+        d_qkv.copy_(g.to(d_qkv.dtype))
+        return d_qkv
+
     # ---- timestep embedding ----
     def time_embed(self, t, freqs, w1, b1, w2, b2, w_all, b_all, scratch, film_all):
         args = t[:, None].float() * freqs[None]

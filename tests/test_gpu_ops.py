@@ -134,6 +134,35 @@ def test_attention_forward_backward(ops, ref, N, S, heads, lo):
     assert rel_l2(r["cuda"][2], r["ref"][2]) < tol
 
 
+@pytest.mark.parametrize("N,S,heads", [(1, 8, 2), (2, 16, 3), (1, 32, 8), (2, 32, 2)])
+def test_attention_flash_forward_backward(ops, ref, N, S, heads):
+    """Fused attention (no materialised probabilities) against the fp32 torch mirror on the same bf16 inputs."""
+    g = G(6)
+    C = heads * 64
+    T = S * S
+    qkv = torch.randn(N, S, S, 3 * C, generator=g).to(torch.bfloat16)
+    d_out = (torch.randn(N, S, S, C, generator=g) * 0.5).to(torch.bfloat16)
+    r = {}
+    for name, o in (("ref", ref), ("cuda", ops)):
+        dev = "cpu" if name == "ref" else DEV
+        out = torch.zeros(N, S, S, C, device=dev, dtype=torch.bfloat16)
+        lse = torch.zeros(N, heads, T, device=dev)
+        o.attention_flash_forward(qkv.to(dev), heads, out, lse)
+        delta = torch.zeros(N, heads, T, device=dev)
+        dq = torch.zeros(N, S, S, 3 * C, device=dev, dtype=torch.bfloat16)
+        # both sides differentiate around the SAME forward output (the reference's bf16-rounded one)
+        o.attention_flash_backward(qkv.to(dev), r["ref"][0].to(dev) if name == "cuda" else out, d_out.to(dev), lse, heads,
+                                   delta, dq)
+        r[name] = (out, lse, delta, dq)
+    f = lambda x: x.float().cpu()
+    assert rel_l2(f(r["cuda"][0]), f(r["ref"][0])) < 1e-2          # P is rounded to bf16 before PV
+    assert (f(r["cuda"][1]) - f(r["ref"][1])).abs().max() < 1e-3   # log-sum-exp (log2 units), fp32 accumulate
+    assert rel_l2(f(r["cuda"][2]), f(r["ref"][2])) < 1e-4
+    dq_c, dq_r = f(r["cuda"][3]).reshape(N, T, heads, 3, 64), f(r["ref"][3]).reshape(N, T, heads, 3, 64)
+    for part in range(3):                                          # dq, dk, dv separately
+        assert rel_l2(dq_c[:, :, :, part], dq_r[:, :, :, part]) < 1.5e-2, part
+
+
 def test_time_embed(ops, ref):
     g = G(7)
     mc, hid, rows, N = 64, 256, 1000, 3
