@@ -419,6 +419,7 @@ int isb_attention_flash_forward(const void* qkv, int N, int T, int heads, int ch
   p.heads = heads;
   p.scale = 1.0f / sqrtf(static_cast<float>(ch));
   p.scale_log2 = p.scale * 1.4426950408889634f;
+  isb::PdlFamily fam(3);
   ISB_CUDA(isb::launch(isb::fa_fwd_kernel, dim3(T / isb::FA_B, heads, N), dim3(128), isb::FA_SMEM_FWD,
                        isb::as_stream(stream), p));
   ISB_LAUNCH_CHECK();
@@ -442,6 +443,7 @@ int isb_attention_flash_backward(const void* qkv, const void* out, const void* d
   p.scale = 1.0f / sqrtf(static_cast<float>(ch));
   p.scale_log2 = p.scale * 1.4426950408889634f;
   const dim3 grid(T / isb::FA_B, heads, N);
+  isb::PdlFamily fam(3);
   ISB_CUDA(isb::launch(isb::fa_bwd_dq_kernel, grid, dim3(128), isb::FA_SMEM_BWD, isb::as_stream(stream), p));
   ISB_LAUNCH_CHECK();
   ISB_CUDA(isb::launch(isb::fa_bwd_dkv_kernel, grid, dim3(128), isb::FA_SMEM_BWD, isb::as_stream(stream), p));

@@ -67,6 +67,15 @@ tensormap_encode_fn get_tensormap_encode();
 // pdl_wait().  ISB_PDL=0 in the environment turns the attribute off (plain stream order).
 bool pdl_enabled();
 bool pdl_enabled_conv();
+// per-family opt-in (ISB_PDL_MASK bit f): 0 GroupNorm statistics / reduce, 1 GroupNorm apply, 2 fused GroupNorm,
+// 3 fused attention, 4 everything else.  The launching function tags its launches with PdlFamily.
+bool pdl_enabled_family(int family);
+extern thread_local int t_pdl_family;
+struct PdlFamily {
+  int prev;
+  explicit PdlFamily(int f) : prev(t_pdl_family) { t_pdl_family = f; }
+  ~PdlFamily() { t_pdl_family = prev; }
+};
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -82,7 +91,7 @@ inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_enabled() || pdl_enabled_family(t_pdl_family)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -301,7 +301,8 @@ __device__ __forceinline__ void epilogue_store4(const EpiDst& e, float4 f, size_
 }
 // `row` = destination row of this lane's accumulator row, `col_base` = destination column of accumulator column 0
 __device__ __forceinline__ void epilogue_direct_warp(const EpiDst& e, int nchunks, uint32_t tmem_base, uint32_t stg,
-                                                     int q, int lane, uint32_t row, bool valid, int col_base) {
+                                                     int q, int lane, uint32_t row, bool valid, int col_base,
+                                                     const unsigned long long* trace = nullptr) {
   const int sub = lane >> 3;
   const int cv = (lane & 7) * 4;
   const uint32_t my_row = stg + static_cast<uint32_t>(lane) * TC_STG_STRIDE;
@@ -312,28 +313,34 @@ __device__ __forceinline__ void epilogue_direct_warp(const EpiDst& e, int nchunk
     uint32_t v[32];
     tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
     tmem_ld_wait();
+    if (c == 0 && q == 2 && lane == 0) tc_stamp(trace, 11);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + static_cast<uint32_t>(j * 16)),
                    "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
                    : "memory");
     __syncwarp();
+    if (c == 0 && q == 2 && lane == 0) tc_stamp(trace, 12);
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + cv));
+    // all eight transposed reads first (back to back), then the dependent shuffle / add / store chains: the
+    // volatile asm keeps program order, so one fused loop serialised load -> store eight times (~110 cycles each)
+    float4 f[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(f[g].x), "=f"(f[g].y), "=f"(f[g].z), "=f"(f[g].w)
+                   : "r"(stg + static_cast<uint32_t>((g * 4 + sub) * TC_STG_STRIDE + cv * 4)));
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int rsel = g * 4 + sub;
-      float4 f;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
-                   : "r"(stg + static_cast<uint32_t>(rsel * TC_STG_STRIDE + cv * 4))
-                   : "memory");
       const uint32_t m_row = __shfl_sync(0xffffffffu, row, rsel);
       if (!((vmask >> rsel) & 1u)) continue;
-      f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
-      epilogue_store4_nb(e, f, static_cast<size_t>(m_row) * e.ld + col0 + cv);
+      f[g].x += b4.x; f[g].y += b4.y; f[g].z += b4.z; f[g].w += b4.w;
+      epilogue_store4_nb(e, f[g], static_cast<size_t>(m_row) * e.ld + col0 + cv);
     }
     __syncwarp();
+    if (c == 0 && q == 2 && lane == 0) tc_stamp(trace, 13);
   }
 }
 
@@ -616,7 +623,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       pe.accumulate = 0;
       pe.col_limit = p.Cout - cout0 < p.block_n ? p.Cout - cout0 : p.block_n;
       epilogue_direct_warp(pe, nchunks, tmem_base, tiles_addr + static_cast<uint32_t>(q) * TC_STG_WARP, q, lane,
-                           static_cast<uint32_t>(r), valid, 0);
+                           static_cast<uint32_t>(r), valid, 0, p.trace);
     } else if (p.splits > 1) {
       // Split-K: every CTA parks its fp32 partial tile in the workspace; the LAST CTA to arrive for this
       // output tile folds all partials in split order (deterministic) and runs the real epilogue.

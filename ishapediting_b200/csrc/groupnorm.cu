@@ -70,11 +70,16 @@ __device__ __forceinline__ bool gn_block_reduce_and_fold(const GnArgs& a, int ng
     is_last = (prev == a.splits - 1);
   }
   __syncthreads();
-  if (!is_last || threadIdx.x != 0) return false;
+  if (!is_last) return false;
   __threadfence();
+  // one partial per thread (independent loads: one L2 round trip in total, not one per partial), summed in order
+  __shared__ double2 folded[GN_MAX_SPLITS];
+  const double2* pp = a.partials + static_cast<size_t>(ng) * GN_MAX_SPLITS;
+  if (static_cast<int>(threadIdx.x) < a.splits) folded[threadIdx.x] = __ldcg(pp + threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x != 0) return false;
   double s0 = 0, s1 = 0;
-  const volatile double2* pp = a.partials + static_cast<size_t>(ng) * GN_MAX_SPLITS;
-  for (int s = 0; s < a.splits; ++s) { s0 += pp[s].x; s1 += pp[s].y; }
+  for (int s = 0; s < a.splits; ++s) { s0 += folded[s].x; s1 += folded[s].y; }
   a.counters[ng] = 0;  // leave the scratch zeroed for the next call
   t0 = s0; t1 = s1;
   return true;
@@ -474,13 +479,22 @@ static cudaError_t launch_cluster_z(void (*kernel)(KArgs...), dim3 grid, dim3 bl
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = cs;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cs > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = cs;
+    ++na;
+  }
+  if (pdl_enabled() || pdl_enabled_family(t_pdl_family)) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = cs > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -544,15 +558,16 @@ int isb_gn_forward(const isb_gn_desc* d, void* scratch, isb_stream_t stream) {
   isb::GnFwdOut o{d->y, d->y_dtype, d->raw, d->raw_dtype, d->xres};
   if (isb::gn_use_fused(a)) {
     const int cs = isb::gn_cluster_size_for(a);
+    isb::PdlFamily fam(2);
     ISB_CUDA(isb::launch_cluster_z(isb::gn_fused_fwd_kernel, dim3(a.groups, a.N, cs), dim3(512), cs, st, a, o));
     ISB_LAUNCH_CHECK();
     return ISB_OK;
   }
-  ISB_CUDA(isb::launch(isb::gn_stats_kernel, dim3(a.splits, a.groups, a.N), 256, 0, st, a));
+  { isb::PdlFamily fam(0); ISB_CUDA(isb::launch(isb::gn_stats_kernel, dim3(a.splits, a.groups, a.N), 256, 0, st, a)); }
   ISB_LAUNCH_CHECK();
   const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;
   const long long total = static_cast<long long>(a.N) * Ho * Wo * (a.C / 8);
-  ISB_CUDA(isb::launch(isb::gn_apply_kernel, isb::cdiv(total, 256), 256, 0, st, a, o));
+  { isb::PdlFamily fam(1); ISB_CUDA(isb::launch(isb::gn_apply_kernel, isb::cdiv(total, 256), 256, 0, st, a, o)); }
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }
@@ -569,14 +584,15 @@ int isb_gn_backward(const isb_gn_bwd_desc* d, void* scratch, isb_stream_t stream
   cudaStream_t st = isb::as_stream(stream);
   if (isb::gn_use_fused(a)) {
     const int cs = isb::gn_cluster_size_for(a);
+    isb::PdlFamily fam(2);
     ISB_CUDA(isb::launch_cluster_z(isb::gn_fused_bwd_kernel, dim3(a.groups, a.N, cs), dim3(512), cs, st, a, b));
     ISB_LAUNCH_CHECK();
     return ISB_OK;
   }
-  ISB_CUDA(isb::launch(isb::gn_bwd_reduce_kernel, dim3(a.splits, a.groups, a.N), 256, 0, st, a, b));
+  { isb::PdlFamily fam(0); ISB_CUDA(isb::launch(isb::gn_bwd_reduce_kernel, dim3(a.splits, a.groups, a.N), 256, 0, st, a, b)); }
   ISB_LAUNCH_CHECK();
   const long long total = static_cast<long long>(a.N) * a.HW * (a.C / 8);
-  ISB_CUDA(isb::launch(isb::gn_bwd_apply_kernel, isb::cdiv(total, 256), 256, 0, st, a, b));
+  { isb::PdlFamily fam(1); ISB_CUDA(isb::launch(isb::gn_bwd_apply_kernel, isb::cdiv(total, 256), 256, 0, st, a, b)); }
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }

@@ -31,6 +31,14 @@ static int pdl_mode() {
   }();
   return mode;
 }
+thread_local int t_pdl_family = 4;
+bool pdl_enabled_family(int family) {
+  static const int mask = [] {
+    const char* e = getenv("ISB_PDL_MASK");
+    return e ? atoi(e) : 0;
+  }();
+  return ((mask >> family) & 1) != 0;
+}
 bool pdl_enabled() { return pdl_mode() == 1; }
 bool pdl_enabled_conv() { return pdl_mode() >= 1; }
 int num_sms() { return g_num_sms; }

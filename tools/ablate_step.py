@@ -13,7 +13,8 @@ from oracle import nfd_oracle as O
 from tests.helpers import build_model
 from ishapediting_b200.drag_utils import DragGeometry, GuidedStepper
 
-FAMILIES = ["conv", "gn_forward", "gn_backward", "attention_forward", "attention_backward", "drag_loss_grad",
+FAMILIES = ["conv", "gn_forward", "gn_backward", "attention_forward", "attention_backward",
+            "attention_flash_forward", "attention_flash_backward", "drag_loss_grad",
             "time_embed", "ddpm_step"]
 
 

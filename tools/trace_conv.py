@@ -10,7 +10,8 @@ import torch
 from ishapediting_b200.ops import CudaOps, PackedWeight
 
 PHASES = ["entry", "prologue done", "producer past pdl_wait", "first stage full", "last MMA committed",
-          "accumulator ready", "tile parked / stored", "cluster sync 1", "fold stored", "exit", "first fold batch summed"]
+          "accumulator ready", "tile parked / stored", "cluster sync 1", "fold stored", "exit", "first fold batch summed",
+          "park: chunk 0 in registers", "park: chunk 0 staged", "park: chunk 0 stored"]
 
 CASES_BIG = [
     (128, 3, 256, 256, {"two_cta": 2, "block_n": 128, "split_k": 1}),
@@ -63,7 +64,7 @@ def main():
             print(f"\nH={H} k{k} {Cin}->{Cout} {tune} debug={dbg}: {ncta} CTAs on {len(set(tr[1,:,15].tolist()))} SMs, "
                   f"launch period {period:.2f} us")
             print(f"  {'phase':26s} {'min':>8s} {'median':>8s} {'max':>8s}   (us after the previous launch's last exit)")
-            for ph in (0, 1, 2, 3, 4, 5, 6, 7, 10, 8, 9):
+            for ph in (0, 1, 2, 3, 4, 5, 11, 12, 13, 6, 7, 10, 8, 9):
                 rel = []
                 for li in range(1, n):
                     base = tr[li - 1, :, 9].max()
