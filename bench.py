@@ -414,7 +414,7 @@ def conv_roofline(st, ds, step_index, geo, feat_layer, use_graph, ms_full_step):
             # dram__bytes_read+write of one captured launch (profiles/r01_ncu_full_conv_tc.md): the 3x3 256->256 @128x128
             # layer moves 9.63 MB = its algorithmic bytes (8.39 MB bf16 activations + 1.18 MB weights; the fp32 output
             # stays in L2)
-            "traffic": 9.63e6, "traffic_launch": "3x3 conv 256->256 @128x128 (19.3 GFLOP)"}
+            "traffic": 9.61e6, "traffic_launch": "3x3 conv 256->256 @128x128 (19.3 GFLOP), profiles/r01_ncu_full_conv_tc_v3.md"}
 
 
 def main():
