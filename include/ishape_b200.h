@@ -92,10 +92,20 @@ typedef struct isb_conv_desc {
   int w_tiled;           /* 1: w is panel-tiled (see above); needs Cout % 64 == 0 */
   int two_cta;           /* 0 heuristic, 1 force the CTA-pair (cta_group::2) kernel, 2 forbid it */
   int debug_flags;       /* profiling only (results become garbage): bit0 skip the TMA loads, bit1 skip the MMAs */
+  /* Optional GroupNorm statistics of the OUTPUT, fused into the epilogue (bf16 path, fp32 out): every CTA writes
+   * the (sum, sum of squares) of its part of each group of gn_cg consecutive output channels; the consumer
+   * (isb_gn_forward with `partials`) folds the gn_slots contributions per (image, group) in fixed order.
+   * This removes the statistics pass of nn.py:16-18 GroupNorm32 over a conv output (unet.py:183,207,285). */
+  float* gn_partials;    /* [N][Cout/gn_cg][gn_slots][2] fp32, or NULL */
+  int gn_cg;             /* channels per group: 8, 16 or 32 (also set it for the isb_conv2d_gn_slots query) */
+  int gn_slots;          /* must equal isb_conv2d_gn_slots(d) */
 } isb_conv_desc;
 /* Workspace (split-K partial tiles + arrival counters): must be ZERO-FILLED by the caller before its
  * first use; every launch leaves the counters at zero again, so one buffer serves all layers. */
 size_t isb_conv2d_workspace(const isb_conv_desc* d);
+/* Contributions per (image, group) the launch described by d writes to gn_partials; 0 = the statistics cannot be
+ * fused for this configuration (the caller then runs the ordinary statistics pass). */
+int isb_conv2d_gn_slots(const isb_conv_desc* d);
 int isb_conv2d(const isb_conv_desc* d, void* workspace, size_t workspace_bytes,
                isb_stream_t stream);
 
@@ -127,6 +137,9 @@ typedef struct isb_gn_desc {
   void* y; int y_dtype;
   void* raw; int raw_dtype;
   float* xres;
+  /* statistics already accumulated by the producer conv (isb_conv_desc.gn_partials): [N][groups][partial_slots][2];
+   * needs x2 == NULL and resample == 0.  NULL = compute them here. */
+  const float* partials; int partial_slots;
 } isb_gn_desc;
 /* scratch: device buffer of isb_gn_scratch_bytes(N, groups) bytes, must be
  * zero-initialised once by the caller and is left zeroed by each call. */

@@ -32,6 +32,7 @@ class ConvDesc(C.Structure):
         ("out", c_void_p), ("out_dtype", c_int), ("Cout", c_int),
         ("accumulate", c_int),
         ("block_n", c_int), ("split_k", c_int), ("stages", c_int), ("w_tiled", c_int), ("two_cta", c_int), ("debug_flags", c_int),
+        ("gn_partials", c_void_p), ("gn_cg", c_int), ("gn_slots", c_int),
     ]
 
 
@@ -48,6 +49,7 @@ class GnDesc(C.Structure):
         ("y", c_void_p), ("y_dtype", c_int),
         ("raw", c_void_p), ("raw_dtype", c_int),
         ("xres", c_void_p),
+        ("partials", c_void_p), ("partial_slots", c_int),
     ]
 
 
@@ -107,6 +109,7 @@ PROTOTYPES = {
     "isb_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "isb_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "isb_conv2d_workspace": (c_size_t, [C.POINTER(ConvDesc)]),
+    "isb_conv2d_gn_slots": (c_int, [C.POINTER(ConvDesc)]),
     "isb_conv2d": (c_int, [C.POINTER(ConvDesc), c_void_p, c_size_t, c_void_p]),
     "isb_gn_scratch_bytes": (c_size_t, [c_int, c_int]),
     "isb_gn_forward": (c_int, [C.POINTER(GnDesc), c_void_p, c_void_p]),

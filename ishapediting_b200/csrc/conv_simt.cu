@@ -6,6 +6,7 @@
 namespace isb {
 
 size_t conv_tc_workspace(const isb_conv_desc* d);
+int conv_tc_gn_slots(const isb_conv_desc* d);
 int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 constexpr int SM_BM = 64, SM_BN = 64, SM_BK = 16, SM_PAD = 4;
@@ -149,6 +150,11 @@ size_t isb_conv2d_workspace(const isb_conv_desc* d) {
   return 0;
 }
 
+int isb_conv2d_gn_slots(const isb_conv_desc* d) {
+  if (d == nullptr || d->a_dtype != ISB_BF16) return 0;    // the fp32 FFMA path computes no fused statistics
+  return isb::conv_tc_gn_slots(d);
+}
+
 int isb_conv2d(const isb_conv_desc* d, void* workspace, size_t workspace_bytes, isb_stream_t stream) {
   if (!isb::is_initialised()) {
     isb::set_error("isb_conv2d: isb_init() has not been called");
@@ -157,6 +163,7 @@ int isb_conv2d(const isb_conv_desc* d, void* workspace, size_t workspace_bytes, 
   ISB_CHECK_ARG(d != nullptr && d->a != nullptr && d->w != nullptr && d->out != nullptr, "isb_conv2d: null pointer");
   if (d->a_dtype == ISB_BF16) return isb::conv_tc_launch(d, workspace, workspace_bytes, isb::as_stream(stream));
   ISB_CHECK_ARG(d->a_dtype == ISB_F32, "isb_conv2d: bad a_dtype %d", d->a_dtype);
+  ISB_CHECK_ARG(d->gn_partials == nullptr, "isb_conv2d: fused GroupNorm statistics need the bf16 path");
   return isb::conv_simt_launch(d, isb::as_stream(stream));
 }
 

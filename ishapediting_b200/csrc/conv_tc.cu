@@ -47,6 +47,10 @@ struct TcParams {
   float* partial;  // != nullptr when splits > 1: [tile][split][128][block_n] fp32
   int* counters;   // [tiles] arrival counters (zero between launches)
   unsigned long long* trace;  // profiling only (debug bit2): [cta][16] %globaltimer stamps of the pipeline phases
+  // GroupNorm statistics of the output, fused into the epilogue: every CTA writes the (sum, sum of squares) of its
+  // part of each group of 2^gn_cg_log2 consecutive output channels to gn_part[n][group][slot] (no atomics).
+  float* gn_part;
+  int gn_cg_log2, gn_slots, gn_groups;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------
@@ -264,6 +268,7 @@ __device__ __forceinline__ void epilogue_store8(const TcParams& p, float* f, siz
 // bias / residual / accumulate are applied on the coalesced side.
 constexpr int TC_STG_STRIDE = 36 * 4;                  // bytes per staged row
 constexpr int TC_STG_WARP = 32 * TC_STG_STRIDE;        // 4608 B per warp
+constexpr uint32_t TC_GN_STAGE_OFF = 4 * TC_STG_WARP;  // 2 KB of statistic partials behind the four transpose buffers
 struct EpiDst {
   void* out;              // row-major [rows][ld]
   int dtype, ld;
@@ -271,9 +276,12 @@ struct EpiDst {
   const float* residual;  // same layout as out (fp32), or nullptr
   int accumulate;
   int col_limit;          // columns >= col_limit do not exist (multiple of 32)
+  uint32_t gn_sm;         // != 0: shared-memory staging [4 warps][8 chunks][4 groups] float2 for the fused statistics
+  int cg_log2;
 };
-// residual (+ previous out) and store 4 consecutive channels at element offset `off` (bias already added)
-__device__ __forceinline__ void epilogue_store4_nb(const EpiDst& e, float4 f, size_t off) {
+// residual (+ previous out) and store 4 consecutive channels at element offset `off` (bias already added);
+// returns the stored fp32 value (the statistics are taken over what the consumer will read)
+__device__ __forceinline__ float4 epilogue_store4_nb(const EpiDst& e, float4 f, size_t off) {
   if (e.residual != nullptr) {
     const float4 r4 = __ldg(reinterpret_cast<const float4*>(e.residual + off));
     f.x += r4.x; f.y += r4.y; f.z += r4.z; f.w += r4.w;
@@ -291,13 +299,14 @@ __device__ __forceinline__ void epilogue_store4_nb(const EpiDst& e, float4 f, si
     u.y = pack_bf16x2(f.z, f.w);
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = u;
   }
+  return f;
 }
-__device__ __forceinline__ void epilogue_store4(const EpiDst& e, float4 f, size_t off, int col) {
+__device__ __forceinline__ float4 epilogue_store4(const EpiDst& e, float4 f, size_t off, int col) {
   if (e.bias != nullptr) {
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
     f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
   }
-  epilogue_store4_nb(e, f, off);
+  return epilogue_store4_nb(e, f, off);
 }
 // `row` = destination row of this lane's accumulator row, `col_base` = destination column of accumulator column 0
 __device__ __forceinline__ void epilogue_direct_warp(const EpiDst& e, int nchunks, uint32_t tmem_base, uint32_t stg,
@@ -331,16 +340,108 @@ __device__ __forceinline__ void epilogue_direct_warp(const EpiDst& e, int nchunk
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                    : "=f"(f[g].x), "=f"(f[g].y), "=f"(f[g].z), "=f"(f[g].w)
                    : "r"(stg + static_cast<uint32_t>((g * 4 + sub) * TC_STG_STRIDE + cv * 4)));
+    float gs = 0.f, gq = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int rsel = g * 4 + sub;
       const uint32_t m_row = __shfl_sync(0xffffffffu, row, rsel);
       if (!((vmask >> rsel) & 1u)) continue;
       f[g].x += b4.x; f[g].y += b4.y; f[g].z += b4.z; f[g].w += b4.w;
-      epilogue_store4_nb(e, f[g], static_cast<size_t>(m_row) * e.ld + col0 + cv);
+      const float4 o4 = epilogue_store4_nb(e, f[g], static_cast<size_t>(m_row) * e.ld + col0 + cv);
+      gs += (o4.x + o4.y) + (o4.z + o4.w);
+      gq = fmaf(o4.x, o4.x, fmaf(o4.y, o4.y, fmaf(o4.z, o4.z, fmaf(o4.w, o4.w, gq))));
+    }
+    if (e.gn_sm != 0) {
+      // the 32 rows of this warp: fold the four row-subsets, then the cg/4 lanes that share a group
+      gs += __shfl_xor_sync(0xffffffffu, gs, 8);  gq += __shfl_xor_sync(0xffffffffu, gq, 8);
+      gs += __shfl_xor_sync(0xffffffffu, gs, 16); gq += __shfl_xor_sync(0xffffffffu, gq, 16);
+      const int lanes_per_group = 1 << (e.cg_log2 - 2);
+      for (int w = 1; w < lanes_per_group; w <<= 1) {
+        gs += __shfl_xor_sync(0xffffffffu, gs, w);
+        gq += __shfl_xor_sync(0xffffffffu, gq, w);
+      }
+      if (sub == 0 && (lane & (lanes_per_group - 1)) == 0)
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(e.gn_sm + static_cast<uint32_t>(((q * 8 + c) * 4 + (lane >> (e.cg_log2 - 2))) * 8)),
+                     "f"(gs), "f"(gq)
+                     : "memory");
     }
     __syncwarp();
     if (c == 0 && q == 2 && lane == 0) tc_stamp(trace, 13);
+  }
+}
+
+// ---- GroupNorm statistics of the conv output (fused; see TcParams::gn_part) ----------------------------------
+// slot of this CTA's contribution within its image(s)
+__device__ __forceinline__ int gn_slot(const TcParams& p, int tile_w, int tile_h, int split) {
+  const int per_tile = p.cluster ? p.splits : 1;
+  return (p.nb == 1 ? (tile_h * p.tiles_w + tile_w) * per_tile : 0) + (p.cluster ? split : 0);
+}
+// direct epilogue: the four warps' staged sums -> gn_part (threads et = 0..127, all must call)
+__device__ __forceinline__ void gn_flush_direct(const TcParams& p, uint32_t gn_sm, int et, int n0, int cout0, int slot) {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  int cols = p.Cout - cout0;
+  if (cols > p.block_n) cols = p.block_n;
+  const int ngroups = cols >> p.gn_cg_log2;
+  const int gpc = 32 >> p.gn_cg_log2;        // groups per 32-column chunk
+  const int warps_per_img = 4 / p.nb;        // nb = 1 or 2 images per 128-row tile
+  for (int i = et; i < ngroups * p.nb; i += 128) {
+    const int img = i / ngroups, gi = i - img * ngroups;
+    if (n0 + img >= p.N) continue;
+    const int c = gi / gpc, k = gi - c * gpc;
+    float s = 0.f, q = 0.f;
+    for (int w = img * warps_per_img; w < (img + 1) * warps_per_img; ++w) {
+      float a, b;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(gn_sm + static_cast<uint32_t>(((w * 8 + c) * 4 + k) * 8)) : "memory");
+      s += a;
+      q += b;
+    }
+    float2* dst = reinterpret_cast<float2*>(p.gn_part) +
+                  (static_cast<size_t>(n0 + img) * p.gn_groups + (cout0 >> p.gn_cg_log2) + gi) * p.gn_slots + slot;
+    *dst = make_float2(s, q);
+  }
+}
+// split-K fold: every thread owns one 4-channel vector (fixed) over some rows of ONE image
+__device__ __forceinline__ void gn_flush_fold(const TcParams& p, uint32_t gn_sm, int et, float gs, float gq, int n0,
+                                              int my_img, bool has_rows, int cout0, int slot) {
+  const int vec_per_row = p.block_n / 4;     // 16, 32 or 64
+  const int lanes_per_group = 1 << (p.gn_cg_log2 - 2);
+  for (int w = 1; w < lanes_per_group; w <<= 1) {
+    gs += __shfl_xor_sync(0xffffffffu, gs, w);
+    gq += __shfl_xor_sync(0xffffffffu, gq, w);
+  }
+  for (int w = vec_per_row; w < 32; w <<= 1) {   // several rows per warp instruction (block_n = 64)
+    gs += __shfl_xor_sync(0xffffffffu, gs, w);
+    gq += __shfl_xor_sync(0xffffffffu, gq, w);
+  }
+  const int warp = et >> 5, lane = et & 31;
+  const int span = vec_per_row < 32 ? vec_per_row : 32;                  // vectors covered by one warp
+  const int v0 = vec_per_row > 32 ? (32 * warp) % vec_per_row : 0;       // first vector of this warp
+  if (lane < span && (lane & (lanes_per_group - 1)) == 0) {
+    const int gi = (v0 + lane) >> (p.gn_cg_log2 - 2);
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(gn_sm + static_cast<uint32_t>((warp * 64 + gi) * 8)), "f"(gs), "f"(gq) : "memory");
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  int cols = p.Cout - cout0;
+  if (cols > p.block_n) cols = p.block_n;
+  const int ngroups = cols >> p.gn_cg_log2;
+  for (int gi = et; gi < ngroups; gi += 128) {
+    const int v = gi << (p.gn_cg_log2 - 2);
+    float s = 0.f, q = 0.f;
+    for (int w = 0; w < 4; ++w) {
+      const int wv0 = vec_per_row > 32 ? (32 * w) % vec_per_row : 0;
+      if (v < wv0 || v >= wv0 + span) continue;
+      float a, b;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(gn_sm + static_cast<uint32_t>((w * 64 + gi) * 8)) : "memory");
+      s += a;
+      q += b;
+    }
+    for (int img = 0; img < p.nb; ++img) {
+      if (n0 + img >= p.N) continue;
+      const bool mine = has_rows && img == my_img;
+      float2* dst = reinterpret_cast<float2*>(p.gn_part) +
+                    (static_cast<size_t>(n0 + img) * p.gn_groups + (cout0 >> p.gn_cg_log2) + gi) * p.gn_slots + slot;
+      *dst = mine ? make_float2(s, q) : make_float2(0.f, 0.f);
+    }
   }
 }
 
@@ -351,7 +452,7 @@ __device__ __forceinline__ void epilogue_direct_warp(const EpiDst& e, int nchunk
 // shared memory through DSMEM: the phase trace showed ~6 B/cycle/SM, 3-8 us per launch; L2 sustains 10x that.)
 template <int S>
 __device__ __forceinline__ void cluster_fold(const TcParams& p, const EpiDst& e, const float* tile_base, int split,
-                                             int et, int n0, int h0, int w0, int cout0) {
+                                             int et, int n0, int h0, int w0, int cout0, int gn_slot_fold) {
   constexpr int U = 16 / S;
   const int per_img = p.tw * p.th;
   int valid_rows = (p.N - n0) * per_img;
@@ -363,6 +464,7 @@ __device__ __forceinline__ void cluster_fold(const TcParams& p, const EpiDst& e,
   const int vec_per_row = p.block_n / 4;
   const int nvec = rows * vec_per_row;          // <= 0 when this rank owns no valid row
   const size_t tile_elems = static_cast<size_t>(TC_BLOCK_M) * p.block_n;
+  float gs = 0.f, gq = 0.f;
   for (int base = et; base < nvec; base += 128 * U) {
     float4 buf[U][S];
     int rr[U], cc[U];
@@ -394,9 +496,13 @@ __device__ __forceinline__ void cluster_fold(const TcParams& p, const EpiDst& e,
       const int rh = rrem >> p.tw_log2;
       const int rw = rrem & (p.tw - 1);
       const size_t mm = (static_cast<size_t>(n0 + rn) * p.H + (h0 + rh)) * p.W + (w0 + rw);
-      epilogue_store4(e, f, mm * p.Cout + col, col);
+      const float4 o4 = epilogue_store4(e, f, mm * p.Cout + col, col);
+      gs += (o4.x + o4.y) + (o4.z + o4.w);
+      gq = fmaf(o4.x, o4.x, fmaf(o4.y, o4.y, fmaf(o4.z, o4.z, fmaf(o4.w, o4.w, gq))));
     }
   }
+  if (p.gn_part != nullptr)
+    gn_flush_fold(p, e.gn_sm, et, gs, gq, n0, rows > 0 ? row0 >> p.pi_log2 : 0, rows > 0, cout0, gn_slot_fold);
 }
 
 // ---- the kernel -------------------------------------------------------------
@@ -446,6 +552,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   out_dst.residual = p.residual;
   out_dst.accumulate = p.accumulate;
   out_dst.col_limit = p.Cout;
+  out_dst.gn_sm = p.gn_part != nullptr ? tiles_addr + TC_GN_STAGE_OFF : 0u;
+  out_dst.cg_log2 = p.gn_cg_log2;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -622,6 +730,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       pe.residual = nullptr;
       pe.accumulate = 0;
       pe.col_limit = p.Cout - cout0 < p.block_n ? p.Cout - cout0 : p.block_n;
+      pe.gn_sm = 0;
+      pe.cg_log2 = 0;
       epilogue_direct_warp(pe, nchunks, tmem_base, tiles_addr + static_cast<uint32_t>(q) * TC_STG_WARP, q, lane,
                            static_cast<uint32_t>(r), valid, 0, p.trace);
     } else if (p.splits > 1) {
@@ -655,6 +765,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (do_final && p.splits == 1) {
       epilogue_direct_warp(out_dst, nchunks, tmem_base, tiles_addr + static_cast<uint32_t>(q) * TC_STG_WARP, q, lane,
                            static_cast<uint32_t>(m), valid, cout0);
+      if (p.gn_part != nullptr)
+        gn_flush_direct(p, out_dst.gn_sm, static_cast<int>(threadIdx.x) - 64, n0, cout0, gn_slot(p, tile_w, tile_h, 0));
     } else if (do_final) {
       // fold: the 128 epilogue threads sweep the tile as a flat array (coalesced 32 B per thread),
       // summing the partials in split order
@@ -695,9 +807,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int et = threadIdx.x - 64;
       const size_t tile_id = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
       const float* tile_base = p.partial + tile_id * p.splits * static_cast<size_t>(TC_BLOCK_M) * p.block_n;
-      if (p.splits == 2) cluster_fold<2>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0);
-      else if (p.splits == 4) cluster_fold<4>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0);
-      else cluster_fold<8>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0);
+      if (p.splits == 2) cluster_fold<2>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0, gn_slot(p, tile_w, tile_h, split));
+      else if (p.splits == 4) cluster_fold<4>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0, gn_slot(p, tile_w, tile_h, split));
+      else cluster_fold<8>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0, gn_slot(p, tile_w, tile_h, split));
     }
     if (threadIdx.x == 64) tc_stamp(p.trace, 8);
   }
@@ -752,6 +864,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   out_dst.residual = p.residual;
   out_dst.accumulate = p.accumulate;
   out_dst.col_limit = p.Cout;
+  out_dst.gn_sm = p.gn_part != nullptr ? tiles_addr + TC_GN_STAGE_OFF : 0u;
+  out_dst.cg_log2 = p.gn_cg_log2;
   const int niter = p.k_iters;
   if (threadIdx.x == 0) {
     tc_stamp(p.trace, 0);
@@ -893,6 +1007,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     pdl_wait();
     epilogue_direct_warp(out_dst, p.block_n / 32, tmem_base, tiles_addr + static_cast<uint32_t>(q) * TC_STG_WARP, q,
                          lane, static_cast<uint32_t>(m), valid, cout0);
+    if (p.gn_part != nullptr)
+      gn_flush_direct(p, out_dst.gn_sm, static_cast<int>(threadIdx.x) - 64, n0, cout0, gn_slot(p, tile_w, tile_h, 0));
   }
 
   if (threadIdx.x == 64) tc_stamp(p.trace, 6);
@@ -912,6 +1028,7 @@ void conv_tc_set_trace(void* ptr) { g_trace = ptr; }
 
 struct TcPlan {
   TcParams p;
+  int gn_slots;     // contributions per (image, group) this launch writes when gn statistics are fused (0: unsupported)
   int smem_bytes;
   size_t ws_bytes;
   size_t counter_bytes;
@@ -1041,6 +1158,22 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   p.w_tiled = d->w_tiled;
   p.debug = d->debug_flags;
   p.trace = nullptr;
+  // fused GroupNorm statistics: groups of 8/16/32 channels inside power-of-two N tiles, cluster or no split
+  p.gn_part = nullptr;
+  p.gn_cg_log2 = 0;
+  p.gn_groups = 0;
+  plan->gn_slots = 0;
+  if (d->gn_cg == 8 || d->gn_cg == 16 || d->gn_cg == 32) {
+    const bool ok = (bn == 64 || bn == 128 || bn == 256) && d->Cout % bn == 0 && (splits == 1 || p.cluster) &&
+                    d->out_dtype == ISB_F32 && p.nb <= 2;
+    if (ok) {
+      plan->gn_slots = (p.nb == 1 ? p.tiles_w * p.tiles_h : 1) * (p.cluster ? splits : 1);
+      p.gn_cg_log2 = d->gn_cg == 8 ? 3 : d->gn_cg == 16 ? 4 : 5;
+      p.gn_groups = d->Cout / d->gn_cg;
+      p.gn_slots = d->gn_slots;
+      p.gn_part = d->gn_partials;
+    }
+  }
   return ISB_OK;
 }
 
@@ -1104,6 +1237,12 @@ int conv_tc_init() {
   return ISB_OK;
 }
 
+int conv_tc_gn_slots(const isb_conv_desc* d) {
+  TcPlan plan;
+  if (plan_tc(d, &plan) != ISB_OK) return 0;
+  return plan.gn_slots;
+}
+
 size_t conv_tc_workspace(const isb_conv_desc* d) {
   TcPlan plan;
   if (plan_tc(d, &plan) != ISB_OK) return 0;
@@ -1120,6 +1259,10 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
                     (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
                 "conv_tc: pointers must be 16-byte aligned");
   TcParams& p = plan.p;
+  if (d->gn_partials != nullptr) {
+    ISB_CHECK_ARG(plan.gn_slots > 0, "conv_tc: GroupNorm statistics cannot be fused for this launch (gn_cg=%d, block_n=%d, split_k=%d)", d->gn_cg, p.block_n, p.splits);
+    ISB_CHECK_ARG(d->gn_slots == plan.gn_slots, "conv_tc: gn_slots=%d but this launch writes %d per (image, group)", d->gn_slots, plan.gn_slots);
+  }
   if (p.splits > 1) {
     if (ws == nullptr || ws_bytes < plan.ws_bytes) {
       set_error("conv_tc: workspace %zu bytes < required %zu", ws_bytes, plan.ws_bytes);

@@ -200,6 +200,99 @@ gn_apply_kernel(const GnArgs a, const GnFwdOut o) {
   gn_apply_one(a, o, n, h, w, c0, a.stats[(n * a.groups + g) * 2], a.stats[(n * a.groups + g) * 2 + 1]);
 }
 
+// Statistics accumulated by the producer conv's epilogue (isb_conv_desc.gn_partials): ONE launch normalises the
+// tensor.  A CTA owns a block of 32 channels (1, 2 or 4 whole groups: Cg = 32, 16, 8) over a chunk of pixels, so it
+// needs the statistics of at most four groups: it folds their `slots` partials itself, in fixed order (8 threads per
+// group, then the 8 run sums in order), and goes on to apply.  No statistics pass, no finalize launch.
+// grid (pixel chunks, C/32, N), 256 threads: thread t owns channel vector t & 3 of pixels (t >> 2) + 64 j.
+constexpr int GN_PART_UNROLL = 4;
+__global__ void __launch_bounds__(256)
+gn_apply_part_kernel(const GnArgs a, const GnFwdOut o, const float2* __restrict__ partials, int slots, int ppc) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ double2 runs[32];
+  __shared__ float s_mean[4], s_rstd[4];
+  const int tid = threadIdx.x;
+  const int cb = blockIdx.y, n = blockIdx.z;
+  const int gpb = 32 / a.Cg;              // groups in this 32-channel block
+  const int g0 = cb * gpb;
+  const int v = tid & 3, pr = tid >> 2;
+  const int c0 = cb * 32 + v * 8;
+  const int p0 = blockIdx.x * ppc;
+  const int p1 = min(a.HW, p0 + ppc);
+  // everything that does not depend on the statistics is requested first: the first batch of pixels and the affine
+  // parameters travel while the partials are being folded (one L2 round trip instead of three in a row)
+  float x[GN_PART_UNROLL][8];
+#pragma unroll
+  for (int u = 0; u < GN_PART_UNROLL; ++u)
+    if (p0 + pr + u * 64 < p1) load8(a.x1 + (static_cast<size_t>(n) * a.HW + (p0 + pr + u * 64)) * a.C + c0, x[u]);
+  float ga[8], be[8];
+  gn_affine8(a, n, c0, ga, be);
+  if (tid < gpb * 8) {
+    const int gl = tid >> 3, part = tid & 7;
+    const float2* pp = partials + static_cast<size_t>(n * a.groups + g0 + gl) * slots;
+    const int beg = slots * part / 8, end = slots * (part + 1) / 8;
+    double s0 = 0, s1 = 0;
+    int i = beg;
+    for (; i + 4 <= end; i += 4) {
+      float2 w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = __ldcg(pp + i + j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s0 += w[j].x; s1 += w[j].y; }
+    }
+    for (; i < end; ++i) {
+      const float2 w = __ldcg(pp + i);
+      s0 += w.x;
+      s1 += w.y;
+    }
+    runs[tid] = make_double2(s0, s1);
+  }
+  __syncthreads();
+  if (tid < gpb) {
+    double s0 = 0, s1 = 0;
+    for (int k = 0; k < 8; ++k) { s0 += runs[tid * 8 + k].x; s1 += runs[tid * 8 + k].y; }
+    const double m = static_cast<double>(a.HW) * a.Cg;
+    const double mean = s0 / m;
+    double var = s1 / m - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[tid] = static_cast<float>(mean);
+    s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+    if (blockIdx.x == 0) {     // kept for the backward pass
+      a.stats[(n * a.groups + g0 + tid) * 2 + 0] = s_mean[tid];
+      a.stats[(n * a.groups + g0 + tid) * 2 + 1] = s_rstd[tid];
+    }
+  }
+  __syncthreads();
+  const int gl = (v * 8) / a.Cg;
+  const float mean = s_mean[gl], rstd = s_rstd[gl];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {   // z = x * ga' + be'
+    ga[j] *= rstd;
+    be[j] -= mean * ga[j];
+  }
+  for (int p = p0 + pr; p < p1; p += GN_PART_UNROLL * 64) {
+    if (p != p0 + pr) {
+#pragma unroll
+      for (int u = 0; u < GN_PART_UNROLL; ++u)
+        if (p + u * 64 < p1) load8(a.x1 + (static_cast<size_t>(n) * a.HW + (p + u * 64)) * a.C + c0, x[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < GN_PART_UNROLL; ++u)
+      if (p + u * 64 < p1) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(x[u][j], ga[j], be[j]);
+          y[j] = a.silu ? silu_f(z) : z;
+        }
+        const size_t off = (static_cast<size_t>(n) * a.HW + (p + u * 64)) * a.C + c0;
+        store8(o.y, off, o.y_dtype, y);
+        if (o.raw) store8(o.raw, off, o.raw_dtype, x[u]);
+      }
+  }
+}
+
 // ---- thread-block-cluster helpers (the fused kernels below run CS CTAs per (image, group)) -------------
 __device__ __forceinline__ uint32_t gn_cluster_rank() {
   uint32_t r;
@@ -556,6 +649,17 @@ int isb_gn_forward(const isb_gn_desc* d, void* scratch, isb_stream_t stream) {
   ISB_CHECK_ARG(d->y != nullptr, "isb_gn_forward: y missing");
   cudaStream_t st = isb::as_stream(stream);
   isb::GnFwdOut o{d->y, d->y_dtype, d->raw, d->raw_dtype, d->xres};
+  if (d->partials != nullptr) {
+    ISB_CHECK_ARG(d->x2 == nullptr && d->resample == 0 && d->partial_slots > 0 && d->groups == 32 &&
+                      (a.Cg == 8 || a.Cg == 16 || a.Cg == 32),
+                  "isb_gn_forward: fused statistics need a single source, no resample, 32 groups of 8/16/32 channels");
+    const int ppc = 64 * isb::GN_PART_UNROLL;
+    isb::PdlFamily fam(1);
+    ISB_CUDA(isb::launch(isb::gn_apply_part_kernel, dim3(isb::cdiv(a.HW, ppc), a.C / 32, a.N), dim3(256), 0, st, a, o,
+                         reinterpret_cast<const float2*>(d->partials), d->partial_slots, ppc));
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+  }
   if (isb::gn_use_fused(a)) {
     const int cs = isb::gn_cluster_size_for(a);
     isb::PdlFamily fam(2);

@@ -112,10 +112,20 @@ class AttentionBlock(nn.Module):
 # ---------------------------------------------------------------------------------------------
 class _T:
     """A fp32 NHWC 'stream' tensor (block input/output) with its gradient buffers."""
-    __slots__ = ("val", "grad", "grad_lo", "has_grad", "name")
+    __slots__ = ("val", "grad", "grad_lo", "has_grad", "name", "gn_slots", "gn_part")
 
-    def __init__(self, val, name):
+    def __init__(self, val, name, gn_slots=0):
         self.val, self.grad, self.grad_lo, self.has_grad, self.name = val, None, None, False, name
+        # GroupNorm statistics fused into the producing conv's epilogue: `gn_slots` = what that conv can deliver
+        # (0: nothing); the first consumer whose GroupNorm reads this tensor alone allocates `gn_part`, which
+        # switches the producer on.
+        self.gn_slots, self.gn_part = gn_slots, None
+
+    def want_gn_part(self, ops):
+        if self.gn_slots > 0 and self.gn_part is None:
+            N = self.val.shape[0]
+            self.gn_part = ops.zeros((N, 32, self.gn_slots, 2))
+        return self.gn_part
 
 
 def _pack3(w, lo):      # [Co,Ci,3,3] -> [Co, 9*Ci], k = (kh*3+kw)*Ci + ci
@@ -174,8 +184,13 @@ class _ResLayer:
         self.xraw = ops.empty((N, H, W, Cin), lo) if self.has_skip_conv else None
         self.xres = ops.empty((N, Ho, Wo, Cin)) if self.resample else None
         self.h1 = ops.empty((N, Ho, Wo, Co))
+        s1 = ops.conv_gn_slots(N, Ho, Wo, Cin, 3, Co)          # GN2 reads conv1's output: statistics from its epilogue
+        self.h1_part = ops.zeros((N, 32, s1, 2)) if s1 > 0 else None
         self.a2 = plan.scratch("a", (N, Ho, Wo, Co), lo)
-        self.out = _T(ops.empty((N, Ho, Wo, Co)), name)
+        self.out = _T(ops.empty((N, Ho, Wo, Co)), name,
+                      ops.conv_gn_slots(N, Ho, Wo, Co, 3, Co, Cin if self.has_skip_conv else 0))
+        # GN1 over a single, un-resampled source whose producer can deliver the statistics
+        self.x_part = srcs[0].want_gn_part(ops) if (len(srcs) == 1 and self.resample == 0) else None
         self.dims = (N, H, W, Cin, Ho, Wo, Co)
 
     def forward(self):
@@ -183,13 +198,15 @@ class _ResLayer:
         x1 = self.srcs[0].val
         x2 = self.srcs[1].val if len(self.srcs) > 1 else None
         ops.gn_forward(x1, x2, self.g1, self.be1, None, 0, True, self.resample, self.stats1, self.a1,
-                       raw=self.xraw, xres=self.xres)
-        ops.conv(self.a1, self.w1, self.b1, 3, self.h1)
-        ops.gn_forward(self.h1, None, self.g2, self.be2, film, self.film_off, True, 0, self.stats2, self.a2)
+                       raw=self.xraw, xres=self.xres, partials=self.x_part)
+        ops.conv(self.a1, self.w1, self.b1, 3, self.h1, gn_part=self.h1_part)
+        ops.gn_forward(self.h1, None, self.g2, self.be2, film, self.film_off, True, 0, self.stats2, self.a2,
+                       partials=self.h1_part)
         if self.has_skip_conv:
-            ops.conv(self.a2, self.w2, self.b2, 3, self.out.val, a2=self.xraw)
+            ops.conv(self.a2, self.w2, self.b2, 3, self.out.val, a2=self.xraw, gn_part=self.out.gn_part)
         else:
-            ops.conv(self.a2, self.w2, self.b2, 3, self.out.val, residual=self.xres if self.resample else x1)
+            ops.conv(self.a2, self.w2, self.b2, 3, self.out.val, residual=self.xres if self.resample else x1,
+                     gn_part=self.out.gn_part)
 
     def backward(self):
         plan, ops, lo = self.plan, self.plan.ops, self.plan.lo
@@ -262,18 +279,19 @@ class _AttnLayer:
             self.qkv = ops.empty((N, H, W, 3 * Cc))
             self.probs = ops.empty((N, self.heads, T, T))
             self.o = plan.scratch("o", (N, H, W, Cc), lo)
-        self.out = _T(ops.empty((N, H, W, Cc)), name)
+        self.out = _T(ops.empty((N, H, W, Cc)), name, ops.conv_gn_slots(N, H, W, Cc, 1, Cc))
+        self.x_part = src.want_gn_part(ops)
         self.dims = (N, H, W, Cc, T)
 
     def forward(self):
         ops, x = self.plan.ops, self.src.val
-        ops.gn_forward(x, None, self.g, self.be, None, 0, False, 0, self.stats, self.a)
+        ops.gn_forward(x, None, self.g, self.be, None, 0, False, 0, self.stats, self.a, partials=self.x_part)
         ops.conv(self.a, self.wqkv, self.bqkv, 1, self.qkv)
         if self.flash:
             ops.attention_flash_forward(self.qkv, self.heads, self.o, self.lse)
         else:
             ops.attention_forward(self.qkv, self.heads, self.probs, self.o)
-        ops.conv(self.o, self.wproj, self.bproj, 1, self.out.val, residual=x)
+        ops.conv(self.o, self.wproj, self.bproj, 1, self.out.val, residual=x, gn_part=self.out.gn_part)
 
     def backward(self):
         plan, ops, lo = self.plan, self.plan.ops, self.plan.lo
@@ -342,7 +360,8 @@ class _Plan:
             self.w_in_d = ops.pack_weight(_pack3_dgrad(w0, lo))
         self.x_nchw = ops.empty((N, Cin, H, W))
         self.x_lo = ops.empty((N, H, W, self.cin_pad), lo)
-        self.h0 = _T(ops.empty((N, H, W, conv0.weight.shape[0])), "input_blocks.0")
+        self.h0 = _T(ops.empty((N, H, W, conv0.weight.shape[0])), "input_blocks.0",
+                     ops.conv_gn_slots(N, H, W, self.cin_pad, 3, conv0.weight.shape[0]))
 
         def add_block(seq, srcs, prefix):
             cur = srcs
@@ -370,6 +389,7 @@ class _Plan:
             h = add_block(blk, [h, hs.pop()], f"output_blocks.{i}")
             self.block_out.append(h)
         self.h_last = h
+        self.out_part = h.want_gn_part(ops)
 
         # --- out (unet.py:612-616) ---
         gn, conv = model.out[0], model.out[2]
@@ -418,7 +438,7 @@ class _Plan:
         if not self.film_external:     # GuidedStepper caches the per-timestep FiLM rows and fills film_all itself
             self.compute_film()
         ops.to_nhwc(self.x_nchw, self.x_lo)
-        ops.conv(self.x_lo, self.w_in, self.b_in, 3, self.h0.val)
+        ops.conv(self.x_lo, self.w_in, self.b_in, 3, self.h0.val, gn_part=self.h0.gn_part)
         inter = self.block_out[feat_layer] if feat_layer >= 0 else None
         stop_after = inter if (upto_feat_only and inter is not None) else None
         self._tail_from = len(self.layers)
@@ -432,7 +452,8 @@ class _Plan:
 
     def forward_out_layer(self):
         ops = self.ops
-        ops.gn_forward(self.h_last.val, None, self.out_g, self.out_b, None, 0, True, 0, self.out_stats, self.out_a)
+        ops.gn_forward(self.h_last.val, None, self.out_g, self.out_b, None, 0, True, 0, self.out_stats, self.out_a,
+                       partials=self.out_part)
         ops.conv(self.out_a, self.w_out, self.b_out, 3, self.out_nhwc)
 
     def forward_tail(self):

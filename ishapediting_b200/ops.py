@@ -144,8 +144,23 @@ class CudaOps:
             return PackedWeight(t, cout, k, True)
         return PackedWeight(w2d.contiguous(), cout, k, False)
 
-    def conv(self, a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None):
-        """a [N,H,W,Cin], w PackedWeight (or a plain [Cout, k*k*Cin (+Cin2)] tensor), out [N,H,W,Cout]."""
+    def conv_gn_slots(self, N, H, W, Cin, ksize, Cout, Cin2=0, groups=32):
+        """Contributions per (image, group) a bf16 conv of this shape writes when the GroupNorm statistics of its
+        output are fused into its epilogue; 0 = not fusable (fp32 mode, group width other than 8/16/32, ...)."""
+        if self.lo != torch.bfloat16 or Cout % groups or os.environ.get("ISB_GN_FUSE", "1") == "0":
+            return 0
+        d = _lib.ConvDesc()
+        d.a, d.a_dtype, d.w, d.out, d.out_dtype = 256, BF16, 256, 256, F32      # pointers only need to be non-null
+        d.N, d.H, d.W, d.Cin, d.ksize, d.Cout = N, H, W, Cin, ksize, Cout
+        if Cin2:
+            d.a2, d.Cin2 = 256, Cin2
+        d.gn_cg = Cout // groups
+        return int(self.lib.isb_conv2d_gn_slots(C.byref(d)))
+
+    def conv(self, a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None, gn_part=None):
+        """a [N,H,W,Cin], w PackedWeight (or a plain [Cout, k*k*Cin (+Cin2)] tensor), out [N,H,W,Cout].
+        gn_part: optional fp32 [N, groups, slots, 2] buffer (slots = conv_gn_slots(...)) that receives the GroupNorm
+        statistics partials of `out`."""
         tiled = False
         if isinstance(w, PackedWeight):
             wshape, tiled, w = (w.cout, w.k), w.tiled, w.data
@@ -175,6 +190,10 @@ class CudaOps:
             d.block_n, d.split_k, d.stages = tune.get("block_n", 0), tune.get("split_k", 0), tune.get("stages", 0)
             d.two_cta = tune.get("two_cta", 0)
             d.debug_flags = tune.get("debug", 0)
+        if gn_part is not None:
+            _chk(gn_part, torch.float32)
+            assert gn_part.shape[0] == N and gn_part.shape[3] == 2 and d.Cout % gn_part.shape[1] == 0
+            d.gn_partials, d.gn_cg, d.gn_slots = _p(gn_part), d.Cout // gn_part.shape[1], gn_part.shape[2]
         if tune and tune.get("trace") is not None:      # profiling: debug bit 2 -> phase stamps land in this tensor
             self.lib.isb_debug_set_trace(_p(tune["trace"]))
         ws, ws_bytes = self._workspace(self.lib.isb_conv2d_workspace(C.byref(d)))
@@ -202,8 +221,13 @@ class CudaOps:
         d.stats = _p(_chk(stats, torch.float32))
         return d
 
-    def gn_forward(self, x1, x2, gamma, beta, film, film_off, silu, resample, stats, y, raw=None, xres=None):
+    def gn_forward(self, x1, x2, gamma, beta, film, film_off, silu, resample, stats, y, raw=None, xres=None,
+                   partials=None):
         d = self._gn_desc(x1, x2, gamma, beta, film, film_off, silu, resample, stats)
+        if partials is not None:     # statistics already accumulated by the producer conv (conv(..., gn_part=))
+            _chk(partials, torch.float32)
+            assert x2 is None and resample == 0 and partials.shape[:2] == (x1.shape[0], 32)
+            d.partials, d.partial_slots = _p(partials), partials.shape[2]
         d.y, d.y_dtype = _p(_chk(y)), _DT[y.dtype]
         if raw is not None:
             d.raw, d.raw_dtype = _p(_chk(raw)), _DT[raw.dtype]

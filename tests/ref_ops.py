@@ -63,7 +63,11 @@ class RefOps:
     def pack_weight(self, w2d):
         return w2d.contiguous()
 
-    def conv(self, a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None):
+    def conv_gn_slots(self, N, H, W, Cin, ksize, Cout, Cin2=0, groups=32):
+        # mirror of CudaOps.conv_gn_slots: fusable in bf16 mode for group widths 8/16/32 (3 slots here)
+        return 3 if (self.lo == torch.bfloat16 and Cout % groups == 0 and Cout // groups in (8, 16, 32)) else 0
+
+    def conv(self, a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None, gn_part=None):
         N, H, W, Cin = a.shape
         Cout = out.shape[3]
         kk = ksize * ksize
@@ -80,6 +84,12 @@ class RefOps:
         if accumulate:
             y = y + out.float()
         out.copy_(y.to(out.dtype))
+        if gn_part is not None:      # (sum, sum of squares) per (image, group): everything in slot 0, zeros elsewhere
+            G = gn_part.shape[1]
+            yg = out.float().reshape(N, H * W, G, Cout // G)
+            gn_part.zero_()
+            gn_part[:, :, 0, 0] = yg.sum(dim=(1, 3))
+            gn_part[:, :, 0, 1] = (yg * yg).sum(dim=(1, 3))
         return out
 
     # ---- group norm ----
@@ -100,7 +110,8 @@ class RefOps:
             a, xr = F.interpolate(a, scale_factor=2, mode="nearest"), F.interpolate(x, scale_factor=2, mode="nearest")
         return a, xr
 
-    def gn_forward(self, x1, x2, gamma, beta, film, film_off, silu, resample, stats, y, raw=None, xres=None):
+    def gn_forward(self, x1, x2, gamma, beta, film, film_off, silu, resample, stats, y, raw=None, xres=None,
+                   partials=None):
         x = x1 if x2 is None else torch.cat([x1, x2], dim=3)
         xn = _nchw(x)
         a, xr = self._gn_fn(xn, gamma, beta, film, film_off, silu, resample)
@@ -108,6 +119,13 @@ class RefOps:
         xg = xn.reshape(N, 32, -1)
         stats[..., 0] = xg.mean(-1)
         stats[..., 1] = 1.0 / torch.sqrt(xg.var(-1, unbiased=False) + 1e-5)
+        if partials is not None:     # the producer's partials must describe THIS tensor (catches stale buffers)
+            assert x2 is None and resample == 0
+            m = xg.shape[-1]
+            mean_p = partials[..., 0].sum(-1) / m
+            var_p = partials[..., 1].sum(-1) / m - mean_p * mean_p
+            assert torch.allclose(mean_p, stats[..., 0], atol=1e-4, rtol=1e-4), "stale GroupNorm partials"
+            assert torch.allclose(var_p, xg.var(-1, unbiased=False), atol=1e-4, rtol=1e-3), "stale GroupNorm partials"
         y.copy_(_nhwc(a).to(y.dtype))
         if raw is not None:
             raw.copy_(x.to(raw.dtype))

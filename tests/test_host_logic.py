@@ -86,6 +86,27 @@ def test_bf16_mode_emulation_within_tolerance():
     assert max(rel_l2(o.detach(), o_ref.detach()), rel_l2(f.detach(), f_ref.detach()), rel_l2(xd.grad, xr.grad)) < 2e-2
 
 
+def test_fused_gn_statistics_plan_mid_bf16():
+    """NFD-width model in bf16 emulation: the plan routes GroupNorm statistics through the producer convs (RefOps
+    asserts that every partials buffer a GroupNorm consumes describes exactly the tensor it normalises) and the
+    result stays within the bf16 tolerance, twice in a row (stale buffers would show on the second pass)."""
+    cfg = O.mid_cfg()
+    sd = O.synth_state_dict(cfg)
+    ops = RefOps("bf16")
+    model, _ = build_model(cfg, sd, "bf16", "cpu", ops)
+    g, x, x2, _ = seeded_inputs(cfg)
+    t = torch.tensor([246])
+    for inp in (x, x2):
+        with torch.no_grad():
+            o_ref, f_ref = O.unet_forward(sd, cfg, inp, t, cfg["feat_layer"])
+            o, f = model(inp, t, feat_layer=cfg["feat_layer"])
+        assert max(rel_l2(o, o_ref), rel_l2(f, f_ref)) < 2e-2
+    plan = next(iter(model._plans.values())) if hasattr(model, "_plans") else None
+    if plan is not None:
+        fused = sum(1 for l in plan.layers if getattr(l, "h1_part", None) is not None or getattr(l, "x_part", None) is not None)
+        assert fused > 0
+
+
 def test_diffusion_tables_and_respacing(small):
     _, _, _, diff = small
     sched = O.Schedule(1000, "200")
