@@ -99,6 +99,15 @@ typedef struct isb_conv_desc {
   float* gn_partials;    /* [N][Cout/gn_cg][gn_slots][2] fp32, or NULL */
   int gn_cg;             /* channels per group: 8, 16 or 32 (also set it for the isb_conv2d_gn_slots query) */
   int gn_slots;          /* must equal isb_conv2d_gn_slots(d) */
+  /* gn_mode 2 (default 0/1 = the statistics above): this conv is the backward-data pass that produces dy of a
+   * GroupNorm(+FiLM)(+SiLU) layer whose input gb_x [N,H,W,Cout] fp32 has the output's shape; gn_partials then
+   * receives the two reduction terms of that GroupNorm's backward, sum(dz g') and sum(dz g' xhat) per (image, group)
+   * (dz = dy * silu'(z)), so that isb_gn_backward (with `partials`) needs no reduction pass. */
+  int gn_mode;
+  const float* gb_x; const float* gb_gamma; const float* gb_beta;
+  const float* gb_film; int gb_film_stride;   /* FiLM rows as in isb_gn_desc, or NULL */
+  const float* gb_stats;                       /* [N,groups,2] mean,rstd of the forward pass */
+  int gb_silu;
 } isb_conv_desc;
 /* Workspace (split-K partial tiles + arrival counters): must be ZERO-FILLED by the caller before its
  * first use; every launch leaves the counters at zero again, so one buffer serves all layers. */
@@ -164,6 +173,9 @@ typedef struct isb_gn_bwd_desc {
   float* gx1; int acc1; void* gx1_lo;
   float* gx2; int acc2; void* gx2_lo;
   int lo_dtype;
+  /* reduction terms already accumulated by the dgrad conv that produced dy (isb_conv_desc.gn_mode 2):
+   * [N][groups][partial_slots][2]; needs a single source and no resample.  NULL = reduce here. */
+  const float* partials; int partial_slots;
 } isb_gn_bwd_desc;
 int isb_gn_backward(const isb_gn_bwd_desc* d, void* scratch, isb_stream_t stream);
 

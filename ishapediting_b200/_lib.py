@@ -33,6 +33,8 @@ class ConvDesc(C.Structure):
         ("accumulate", c_int),
         ("block_n", c_int), ("split_k", c_int), ("stages", c_int), ("w_tiled", c_int), ("two_cta", c_int), ("debug_flags", c_int),
         ("gn_partials", c_void_p), ("gn_cg", c_int), ("gn_slots", c_int),
+        ("gn_mode", c_int), ("gb_x", c_void_p), ("gb_gamma", c_void_p), ("gb_beta", c_void_p),
+        ("gb_film", c_void_p), ("gb_film_stride", c_int), ("gb_stats", c_void_p), ("gb_silu", c_int),
     ]
 
 
@@ -61,6 +63,7 @@ class GnBwdDesc(C.Structure):
         ("gx1", c_void_p), ("acc1", c_int), ("gx1_lo", c_void_p),
         ("gx2", c_void_p), ("acc2", c_int), ("gx2_lo", c_void_p),
         ("lo_dtype", c_int),
+        ("partials", c_void_p), ("partial_slots", c_int),
     ]
 
 

@@ -51,6 +51,11 @@ struct TcParams {
   // part of each group of 2^gn_cg_log2 consecutive output channels to gn_part[n][group][slot] (no atomics).
   float* gn_part;
   int gn_cg_log2, gn_slots, gn_groups;
+  // gn_mode 2: the output is dy of a GroupNorm(+SiLU) whose input gb_x has the same shape; the partials are the two
+  // sums of its backward pass, sum(dz*gamma') and sum(dz*gamma'*xhat)  (dz = dy * silu'(z), z = xhat*gamma' + beta')
+  int gn_mode;
+  const float* gb_x; const float* gb_gamma; const float* gb_beta; const float* gb_film; const float* gb_stats;
+  int gb_film_stride, gb_silu;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------
@@ -278,7 +283,43 @@ struct EpiDst {
   int col_limit;          // columns >= col_limit do not exist (multiple of 32)
   uint32_t gn_sm;         // != 0: shared-memory staging [4 warps][8 chunks][4 groups] float2 for the fused statistics
   int cg_log2;
+  const TcParams* gb;     // != nullptr: accumulate the GroupNorm-backward sums instead of (sum, sum of squares)
 };
+// per-lane constants of the GroupNorm-backward terms for 4 consecutive channels of image n
+struct GbConst {
+  float ga[4], be[4], mean, rstd;
+};
+__device__ __forceinline__ void gb_load(const TcParams& p, int n, int c, GbConst& k) {
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gb_gamma + c));
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.gb_beta + c));
+  k.ga[0] = g4.x; k.ga[1] = g4.y; k.ga[2] = g4.z; k.ga[3] = g4.w;
+  k.be[0] = b4.x; k.be[1] = b4.y; k.be[2] = b4.z; k.be[3] = b4.w;
+  if (p.gb_film != nullptr) {
+    const float* f = p.gb_film + static_cast<size_t>(n) * p.gb_film_stride;
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(f + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(f + p.Cout + c));
+    k.ga[0] *= 1.0f + sc.x; k.ga[1] *= 1.0f + sc.y; k.ga[2] *= 1.0f + sc.z; k.ga[3] *= 1.0f + sc.w;
+    k.be[0] = k.be[0] * (1.0f + sc.x) + sh.x; k.be[1] = k.be[1] * (1.0f + sc.y) + sh.y;
+    k.be[2] = k.be[2] * (1.0f + sc.z) + sh.z; k.be[3] = k.be[3] * (1.0f + sc.w) + sh.w;
+  }
+  const int g = c >> p.gn_cg_log2;
+  k.mean = __ldg(p.gb_stats + (n * p.gn_groups + g) * 2);
+  k.rstd = __ldg(p.gb_stats + (n * p.gn_groups + g) * 2 + 1);
+}
+// adds this element vector's contribution: s1 += dz*gamma', s2 += dz*gamma'*xhat
+__device__ __forceinline__ void gb_accumulate(const TcParams& p, const GbConst& k, float4 dy, size_t off, float& s1, float& s2) {
+  const float4 x4 = __ldg(reinterpret_cast<const float4*>(p.gb_x + off));
+  const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ds[4] = {dy.x, dy.y, dy.z, dy.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float xhat = (xs[j] - k.mean) * k.rstd;
+    float d = ds[j];
+    if (p.gb_silu) d *= silu_grad_f(fmaf(xhat, k.ga[j], k.be[j]));
+    const float dzg = d * k.ga[j];
+    s1 += dzg;
+    s2 = fmaf(dzg, xhat, s2);
+  }
+}
 // residual (+ previous out) and store 4 consecutive channels at element offset `off` (bias already added);
 // returns the stored fp32 value (the statistics are taken over what the consumer will read)
 __device__ __forceinline__ float4 epilogue_store4_nb(const EpiDst& e, float4 f, size_t off) {
@@ -311,7 +352,7 @@ __device__ __forceinline__ float4 epilogue_store4(const EpiDst& e, float4 f, siz
 // `row` = destination row of this lane's accumulator row, `col_base` = destination column of accumulator column 0
 __device__ __forceinline__ void epilogue_direct_warp(const EpiDst& e, int nchunks, uint32_t tmem_base, uint32_t stg,
                                                      int q, int lane, uint32_t row, bool valid, int col_base,
-                                                     const unsigned long long* trace = nullptr) {
+                                                     const unsigned long long* trace = nullptr, int gb_n = 0) {
   const int sub = lane >> 3;
   const int cv = (lane & 7) * 4;
   const uint32_t my_row = stg + static_cast<uint32_t>(lane) * TC_STG_STRIDE;
@@ -341,15 +382,22 @@ __device__ __forceinline__ void epilogue_direct_warp(const EpiDst& e, int nchunk
                    : "=f"(f[g].x), "=f"(f[g].y), "=f"(f[g].z), "=f"(f[g].w)
                    : "r"(stg + static_cast<uint32_t>((g * 4 + sub) * TC_STG_STRIDE + cv * 4)));
     float gs = 0.f, gq = 0.f;
+    GbConst gk;
+    if (e.gb != nullptr) gb_load(*e.gb, gb_n, col0 + cv, gk);
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int rsel = g * 4 + sub;
       const uint32_t m_row = __shfl_sync(0xffffffffu, row, rsel);
       if (!((vmask >> rsel) & 1u)) continue;
       f[g].x += b4.x; f[g].y += b4.y; f[g].z += b4.z; f[g].w += b4.w;
-      const float4 o4 = epilogue_store4_nb(e, f[g], static_cast<size_t>(m_row) * e.ld + col0 + cv);
-      gs += (o4.x + o4.y) + (o4.z + o4.w);
-      gq = fmaf(o4.x, o4.x, fmaf(o4.y, o4.y, fmaf(o4.z, o4.z, fmaf(o4.w, o4.w, gq))));
+      const size_t off = static_cast<size_t>(m_row) * e.ld + col0 + cv;
+      const float4 o4 = epilogue_store4_nb(e, f[g], off);
+      if (e.gb != nullptr) {
+        gb_accumulate(*e.gb, gk, o4, off, gs, gq);
+      } else {
+        gs += (o4.x + o4.y) + (o4.z + o4.w);
+        gq = fmaf(o4.x, o4.x, fmaf(o4.y, o4.y, fmaf(o4.z, o4.z, fmaf(o4.w, o4.w, gq))));
+      }
     }
     if (e.gn_sm != 0) {
       // the 32 rows of this warp: fold the four row-subsets, then the cg/4 lanes that share a group
@@ -465,6 +513,12 @@ __device__ __forceinline__ void cluster_fold(const TcParams& p, const EpiDst& e,
   const int nvec = rows * vec_per_row;          // <= 0 when this rank owns no valid row
   const size_t tile_elems = static_cast<size_t>(TC_BLOCK_M) * p.block_n;
   float gs = 0.f, gq = 0.f;
+  GbConst gk;
+  if (e.gb != nullptr) {     // this thread's 4-channel vector is the same in every batch; its rows lie in one image
+    const int my_n = n0 + (rows > 0 ? row0 >> p.pi_log2 : 0);
+    const int my_c = cout0 + (et % vec_per_row) * 4;
+    gb_load(p, my_n < p.N ? my_n : p.N - 1, my_c < p.Cout ? my_c : 0, gk);
+  }
   for (int base = et; base < nvec; base += 128 * U) {
     float4 buf[U][S];
     int rr[U], cc[U];
@@ -497,8 +551,12 @@ __device__ __forceinline__ void cluster_fold(const TcParams& p, const EpiDst& e,
       const int rw = rrem & (p.tw - 1);
       const size_t mm = (static_cast<size_t>(n0 + rn) * p.H + (h0 + rh)) * p.W + (w0 + rw);
       const float4 o4 = epilogue_store4(e, f, mm * p.Cout + col, col);
-      gs += (o4.x + o4.y) + (o4.z + o4.w);
-      gq = fmaf(o4.x, o4.x, fmaf(o4.y, o4.y, fmaf(o4.z, o4.z, fmaf(o4.w, o4.w, gq))));
+      if (e.gb != nullptr) {
+        gb_accumulate(p, gk, o4, mm * p.Cout + col, gs, gq);
+      } else {
+        gs += (o4.x + o4.y) + (o4.z + o4.w);
+        gq = fmaf(o4.x, o4.x, fmaf(o4.y, o4.y, fmaf(o4.z, o4.z, fmaf(o4.w, o4.w, gq))));
+      }
     }
   }
   if (p.gn_part != nullptr)
@@ -554,6 +612,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   out_dst.col_limit = p.Cout;
   out_dst.gn_sm = p.gn_part != nullptr ? tiles_addr + TC_GN_STAGE_OFF : 0u;
   out_dst.cg_log2 = p.gn_cg_log2;
+  out_dst.gb = (p.gn_part != nullptr && p.gn_mode == 2) ? &p : nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -732,6 +791,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       pe.col_limit = p.Cout - cout0 < p.block_n ? p.Cout - cout0 : p.block_n;
       pe.gn_sm = 0;
       pe.cg_log2 = 0;
+      pe.gb = nullptr;
       epilogue_direct_warp(pe, nchunks, tmem_base, tiles_addr + static_cast<uint32_t>(q) * TC_STG_WARP, q, lane,
                            static_cast<uint32_t>(r), valid, 0, p.trace);
     } else if (p.splits > 1) {
@@ -764,7 +824,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     if (do_final && p.splits == 1) {
       epilogue_direct_warp(out_dst, nchunks, tmem_base, tiles_addr + static_cast<uint32_t>(q) * TC_STG_WARP, q, lane,
-                           static_cast<uint32_t>(m), valid, cout0);
+                           static_cast<uint32_t>(m), valid, cout0, nullptr, valid ? n : p.N - 1);
       if (p.gn_part != nullptr)
         gn_flush_direct(p, out_dst.gn_sm, static_cast<int>(threadIdx.x) - 64, n0, cout0, gn_slot(p, tile_w, tile_h, 0));
     } else if (do_final) {
@@ -866,6 +926,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   out_dst.col_limit = p.Cout;
   out_dst.gn_sm = p.gn_part != nullptr ? tiles_addr + TC_GN_STAGE_OFF : 0u;
   out_dst.cg_log2 = p.gn_cg_log2;
+  out_dst.gb = (p.gn_part != nullptr && p.gn_mode == 2) ? &p : nullptr;
   const int niter = p.k_iters;
   if (threadIdx.x == 0) {
     tc_stamp(p.trace, 0);
@@ -1006,7 +1067,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (threadIdx.x == 64) tc_stamp(p.trace, 5);
     pdl_wait();
     epilogue_direct_warp(out_dst, p.block_n / 32, tmem_base, tiles_addr + static_cast<uint32_t>(q) * TC_STG_WARP, q,
-                         lane, static_cast<uint32_t>(m), valid, cout0);
+                         lane, static_cast<uint32_t>(m), valid, cout0, nullptr, valid ? n : p.N - 1);
     if (p.gn_part != nullptr)
       gn_flush_direct(p, out_dst.gn_sm, static_cast<int>(threadIdx.x) - 64, n0, cout0, gn_slot(p, tile_w, tile_h, 0));
   }
@@ -1174,6 +1235,10 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
       p.gn_part = d->gn_partials;
     }
   }
+  p.gn_mode = d->gn_mode == 2 ? 2 : 1;
+  p.gb_x = d->gb_x; p.gb_gamma = d->gb_gamma; p.gb_beta = d->gb_beta; p.gb_film = d->gb_film; p.gb_stats = d->gb_stats;
+  p.gb_film_stride = d->gb_film_stride;
+  p.gb_silu = d->gb_silu;
   return ISB_OK;
 }
 
@@ -1262,6 +1327,8 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
   if (d->gn_partials != nullptr) {
     ISB_CHECK_ARG(plan.gn_slots > 0, "conv_tc: GroupNorm statistics cannot be fused for this launch (gn_cg=%d, block_n=%d, split_k=%d)", d->gn_cg, p.block_n, p.splits);
     ISB_CHECK_ARG(d->gn_slots == plan.gn_slots, "conv_tc: gn_slots=%d but this launch writes %d per (image, group)", d->gn_slots, plan.gn_slots);
+    ISB_CHECK_ARG(d->gn_mode != 2 || (d->gb_x && d->gb_gamma && d->gb_beta && d->gb_stats && (d->gb_film == nullptr || d->gb_film_stride >= 2 * d->Cout)),
+                  "conv_tc: gn_mode 2 needs gb_x, gb_gamma, gb_beta, gb_stats (and gb_film_stride >= 2*Cout with gb_film)");
   }
   if (p.splits > 1) {
     if (ws == nullptr || ws_bytes < plan.ws_bytes) {

@@ -506,6 +506,114 @@ gn_bwd_apply_kernel(const GnArgs a, const GnBwdArgs b) {
   gn_bwd_apply_one(a, b, n, h, w, c0, a.stats[sg * 2], a.stats[sg * 2 + 1], a.bstats[sg * 2], a.bstats[sg * 2 + 1]);
 }
 
+// per-thread constants of the backward kernels: z = xhat * ga + be
+struct GnRowBwdConst {
+  float ga[8], be[8], mean, rstd;
+};
+__device__ __forceinline__ void gn_row_bwd_terms(const GnArgs& a, const GnRowBwdConst& k, const float* x, const float* dy,
+                                                 float* dzg, float* xhat) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    xhat[j] = (x[j] - k.mean) * k.rstd;
+    float d = dy[j];
+    if (a.silu) d *= silu_grad_f(xhat[j] * k.ga[j] + k.be[j]);
+    dzg[j] = d * k.ga[j];
+  }
+}
+
+// Backward with the reduction terms already accumulated by the dgrad conv that produced dy (isb_conv_desc.gn_mode 2):
+// same geometry as gn_apply_part_kernel — a CTA owns 32 channels (<= 4 groups), folds their partials itself and
+// applies.  One launch instead of reduce + apply.
+constexpr int GN_PART_UNROLL_BWD = 2;
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_part_kernel(const GnArgs a, const GnBwdArgs b, const float2* __restrict__ partials, int slots, int ppc) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ double2 runs[32];
+  __shared__ float s_m1[4], s_m2[4];
+  const int tid = threadIdx.x;
+  const int cb = blockIdx.y, n = blockIdx.z;
+  const int gpb = 32 / a.Cg;
+  const int g0 = cb * gpb;
+  const int v = tid & 3, pr = tid >> 2;
+  const int c0 = cb * 32 + v * 8;
+  const int p0 = blockIdx.x * ppc;
+  const int p1 = min(a.HW, p0 + ppc);
+  const bool acc_gx = b.acc1 && b.gx1 != nullptr;
+  float x[GN_PART_UNROLL_BWD][8], dy[GN_PART_UNROLL_BWD][8], rs[GN_PART_UNROLL_BWD][8], old[GN_PART_UNROLL_BWD][8];
+  auto fetch = [&](int p) {
+#pragma unroll
+    for (int u = 0; u < GN_PART_UNROLL_BWD; ++u)
+      if (p + u * 64 < p1) {
+        const size_t off = (static_cast<size_t>(n) * a.HW + (p + u * 64)) * a.C + c0;
+        load8(a.x1 + off, x[u]);
+        load8(b.dy + off, dy[u]);
+        if (b.gres != nullptr) load8(b.gres + off, rs[u]);
+        if (acc_gx) {
+          const float4* q = reinterpret_cast<const float4*>(b.gx1 + off);
+          const float4 u0 = q[0], u1 = q[1];
+          old[u][0] = u0.x; old[u][1] = u0.y; old[u][2] = u0.z; old[u][3] = u0.w;
+          old[u][4] = u1.x; old[u][5] = u1.y; old[u][6] = u1.z; old[u][7] = u1.w;
+        }
+      }
+  };
+  fetch(p0 + pr);     // in flight while the partials are folded
+  GnRowBwdConst k;
+  gn_affine8(a, n, c0, k.ga, k.be);
+  const int sg = n * a.groups + c0 / a.Cg;
+  k.mean = a.stats[sg * 2];
+  k.rstd = a.stats[sg * 2 + 1];
+  if (tid < gpb * 8) {
+    const int gl = tid >> 3, part = tid & 7;
+    const float2* pp = partials + static_cast<size_t>(n * a.groups + g0 + gl) * slots;
+    const int beg = slots * part / 8, end = slots * (part + 1) / 8;
+    double s0 = 0, s1 = 0;
+    int i = beg;
+    for (; i + 4 <= end; i += 4) {
+      float2 w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = __ldcg(pp + i + j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s0 += w[j].x; s1 += w[j].y; }
+    }
+    for (; i < end; ++i) {
+      const float2 w = __ldcg(pp + i);
+      s0 += w.x;
+      s1 += w.y;
+    }
+    runs[tid] = make_double2(s0, s1);
+  }
+  __syncthreads();
+  if (tid < gpb) {
+    double s0 = 0, s1 = 0;
+    for (int q = 0; q < 8; ++q) { s0 += runs[tid * 8 + q].x; s1 += runs[tid * 8 + q].y; }
+    const double m = static_cast<double>(a.HW) * a.Cg;
+    s_m1[tid] = static_cast<float>(s0 / m);
+    s_m2[tid] = static_cast<float>(s1 / m);
+  }
+  __syncthreads();
+  const int gl = (v * 8) / a.Cg;
+  const float m1 = s_m1[gl], m2 = s_m2[gl];
+  for (int p = p0 + pr; p < p1; p += GN_PART_UNROLL_BWD * 64) {
+    if (p != p0 + pr) fetch(p);
+#pragma unroll
+    for (int u = 0; u < GN_PART_UNROLL_BWD; ++u)
+      if (p + u * 64 < p1) {
+        float dzg[8], xhat[8], dx[8];
+        gn_row_bwd_terms(a, k, x[u], dy[u], dzg, xhat);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dx[j] = k.rstd * (dzg[j] - (m1 + xhat[j] * m2));
+          if (b.gres != nullptr) dx[j] += rs[u][j];
+          if (acc_gx) dx[j] += old[u][j];
+        }
+        const size_t off = (static_cast<size_t>(n) * a.HW + (p + u * 64)) * a.C + c0;
+        if (b.gx1 != nullptr) store8(b.gx1, off, ISB_F32, dx);
+        if (b.gx1_lo != nullptr) store8(b.gx1_lo, off, b.lo_dtype, dx);
+      }
+  }
+}
+
 // single-launch backward for small tensors (see gn_fused_fwd_kernel)
 __global__ void __launch_bounds__(512)
 gn_fused_bwd_kernel(const GnArgs a, const GnBwdArgs b) {
@@ -686,6 +794,17 @@ int isb_gn_backward(const isb_gn_bwd_desc* d, void* scratch, isb_stream_t stream
   isb::GnBwdArgs b{d->dy, d->gres, d->gres_at_input, d->gx1, d->acc1, d->gx1_lo,
                    d->gx2, d->acc2, d->gx2_lo, d->lo_dtype};
   cudaStream_t st = isb::as_stream(stream);
+  if (d->partials != nullptr) {
+    ISB_CHECK_ARG(d->f.x2 == nullptr && d->f.resample == 0 && d->partial_slots > 0 && d->f.groups == 32 &&
+                      (a.Cg == 8 || a.Cg == 16 || a.Cg == 32) && d->gx2 == nullptr && d->gx2_lo == nullptr,
+                  "isb_gn_backward: fused reduction terms need a single source, no resample, 32 groups of 8/16/32 channels");
+    const int ppc = 64 * isb::GN_PART_UNROLL_BWD * 2;
+    isb::PdlFamily fam(1);
+    ISB_CUDA(isb::launch(isb::gn_bwd_apply_part_kernel, dim3(isb::cdiv(a.HW, ppc), a.C / 32, a.N), dim3(256), 0, st, a, b,
+                         reinterpret_cast<const float2*>(d->partials), d->partial_slots, ppc));
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+  }
   if (isb::gn_use_fused(a)) {
     const int cs = isb::gn_cluster_size_for(a);
     isb::PdlFamily fam(2);

@@ -12,6 +12,7 @@ gradients, walking only the layers that lie between the requested gradient roots
 from __future__ import annotations
 
 import math
+import os
 
 import torch as th
 import torch.nn as nn
@@ -191,6 +192,13 @@ class _ResLayer:
                       ops.conv_gn_slots(N, Ho, Wo, Co, 3, Co, Cin if self.has_skip_conv else 0))
         # GN1 over a single, un-resampled source whose producer can deliver the statistics
         self.x_part = srcs[0].want_gn_part(ops) if (len(srcs) == 1 and self.resample == 0) else None
+        # backward: the dgrad convs that produce dy of GN2 / GN1 accumulate those layers' reduction terms
+        self.b2_part = self.b1_part = None
+        if plan.want_backward and plan.fuse_gn_bwd:
+            s2 = ops.conv_gn_slots(N, Ho, Wo, Co, 3, Co)
+            self.b2_part = ops.zeros((N, 32, s2, 2)) if s2 > 0 else None
+            s1b = ops.conv_gn_slots(N, H, W, Co, 3, Cin) if (len(srcs) == 1 and self.resample == 0) else 0
+            self.b1_part = ops.zeros((N, 32, s1b, 2)) if s1b > 0 else None
         self.dims = (N, H, W, Cin, Ho, Wo, Co)
 
     def forward(self):
@@ -230,12 +238,14 @@ class _ResLayer:
             at_input = True
         else:
             gres, at_input = g_out, False
-        ops.conv(g_out_lo, self.w2_d, None, 3, g_a2)
+        gn2 = (self.h1, self.g2, self.be2, plan.film_all, self.film_off, True, self.stats2)
+        ops.conv(g_out_lo, self.w2_d, None, 3, g_a2, gn_part=self.b2_part, gn_bwd=gn2 if self.b2_part is not None else None)
         g_h1_lo = plan.scratch("glo", (N, Ho, Wo, Co), lo)
         ops.gn_backward(self.h1, None, self.g2, self.be2, plan.film_all, self.film_off, True, 0, self.stats2,
-                        g_a2, None, False, None, False, g_h1_lo, None, False, None)
+                        g_a2, None, False, None, False, g_h1_lo, None, False, None, partials=self.b2_part)
         g_a1 = plan.scratch("g", (N, Ho, Wo, Cin), th.float32)
-        ops.conv(g_h1_lo, self.w1_d, None, 3, g_a1)
+        gn1 = (self.srcs[0].val, self.g1, self.be1, None, 0, True, self.stats1)
+        ops.conv(g_h1_lo, self.w1_d, None, 3, g_a1, gn_part=self.b1_part, gn_bwd=gn1 if self.b1_part is not None else None)
         if joined is not None:
             th.cuda.current_stream().wait_event(joined)
         s1 = self.srcs[0]
@@ -247,7 +257,7 @@ class _ResLayer:
                         self.stats1, g_a1, gres, at_input,
                         s1.grad, s1.has_grad, s1.grad_lo,
                         s2.grad if s2 is not None else None, s2.has_grad if s2 is not None else False,
-                        s2.grad_lo if s2 is not None else None)
+                        s2.grad_lo if s2 is not None else None, partials=self.b1_part)
         s1.has_grad = True
         if s2 is not None:
             s2.has_grad = True
@@ -281,6 +291,8 @@ class _AttnLayer:
             self.o = plan.scratch("o", (N, H, W, Cc), lo)
         self.out = _T(ops.empty((N, H, W, Cc)), name, ops.conv_gn_slots(N, H, W, Cc, 1, Cc))
         self.x_part = src.want_gn_part(ops)
+        sb = ops.conv_gn_slots(N, H, W, 3 * Cc, 1, Cc) if (plan.want_backward and plan.fuse_gn_bwd) else 0
+        self.b_part = ops.zeros((N, 32, sb, 2)) if sb > 0 else None
         self.dims = (N, H, W, Cc, T)
 
     def forward(self):
@@ -308,11 +320,12 @@ class _AttnLayer:
             tmp = plan.scratch("ptmp", (N, self.heads, T, T), th.float32)
             ops.attention_backward(self.qkv, self.probs, g_o, self.heads, tmp, g_qkv)
         g_a = plan.scratch("g", (N, H, W, Cc), th.float32)
-        ops.conv(g_qkv, self.wqkv_d, None, 1, g_a)
         s = self.src
+        gnb = (s.val, self.g, self.be, None, 0, False, self.stats)
+        ops.conv(g_qkv, self.wqkv_d, None, 1, g_a, gn_part=self.b_part, gn_bwd=gnb if self.b_part is not None else None)
         plan.ensure_grad(s)
         ops.gn_backward(s.val, None, self.g, self.be, None, 0, False, 0, self.stats, g_a, self.out.grad, False,
-                        s.grad, s.has_grad, s.grad_lo, None, False, None)
+                        s.grad, s.has_grad, s.grad_lo, None, False, None, partials=self.b_part)
         s.has_grad = True
 
 
@@ -327,6 +340,10 @@ class _Plan:
         self.layers = []          # execution order, objects with forward()/backward()/out
         self.generation = 0
         self.film_external = False
+        # GroupNorm-backward reduction terms from the dgrad conv's epilogue (ISB_GN_FUSE_BWD=1).  Measured on B200: the
+        # step gets 4 % SLOWER — the terms need x and a SiLU derivative per element, which the four epilogue warps of a
+        # conv CTA do far more slowly than the wide reduction kernel they replace.  Kept behind the switch, tested.
+        self.fuse_gn_bwd = os.environ.get("ISB_GN_FUSE_BWD", "0") == "1"
         self.side = None          # (stream, fork_event, join_event) for branch-level concurrency in the backward
         lo = self.lo
         Cin = model.in_channels

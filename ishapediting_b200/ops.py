@@ -157,10 +157,12 @@ class CudaOps:
         d.gn_cg = Cout // groups
         return int(self.lib.isb_conv2d_gn_slots(C.byref(d)))
 
-    def conv(self, a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None, gn_part=None):
+    def conv(self, a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None, gn_part=None,
+             gn_bwd=None):
         """a [N,H,W,Cin], w PackedWeight (or a plain [Cout, k*k*Cin (+Cin2)] tensor), out [N,H,W,Cout].
         gn_part: optional fp32 [N, groups, slots, 2] buffer (slots = conv_gn_slots(...)) that receives the GroupNorm
-        statistics partials of `out`."""
+        statistics partials of `out`.  gn_bwd = (x, gamma, beta, film, film_off, silu, stats): `out` is dy of that
+        GroupNorm layer and gn_part receives the two reduction terms of its backward instead."""
         tiled = False
         if isinstance(w, PackedWeight):
             wshape, tiled, w = (w.cout, w.k), w.tiled, w.data
@@ -194,6 +196,15 @@ class CudaOps:
             _chk(gn_part, torch.float32)
             assert gn_part.shape[0] == N and gn_part.shape[3] == 2 and d.Cout % gn_part.shape[1] == 0
             d.gn_partials, d.gn_cg, d.gn_slots = _p(gn_part), d.Cout // gn_part.shape[1], gn_part.shape[2]
+            if gn_bwd is not None:
+                gx, gamma, beta, film, film_off, silu, stats = gn_bwd
+                assert gx.shape == out.shape and out.dtype == torch.float32
+                d.gn_mode, d.gb_x = 2, _p(_chk(gx, torch.float32))
+                d.gb_gamma, d.gb_beta = _p(_chk(gamma, torch.float32)), _p(_chk(beta, torch.float32))
+                d.gb_stats, d.gb_silu = _p(_chk(stats, torch.float32)), int(silu)
+                if film is not None:
+                    d.gb_film = C.c_void_p(_chk(film, torch.float32).data_ptr() + 4 * film_off)
+                    d.gb_film_stride = film.shape[1]
         if tune and tune.get("trace") is not None:      # profiling: debug bit 2 -> phase stamps land in this tensor
             self.lib.isb_debug_set_trace(_p(tune["trace"]))
         ws, ws_bytes = self._workspace(self.lib.isb_conv2d_workspace(C.byref(d)))
@@ -237,8 +248,12 @@ class CudaOps:
         return y
 
     def gn_backward(self, x1, x2, gamma, beta, film, film_off, silu, resample, stats, dy, gres, gres_at_input,
-                    gx1, acc1, gx1_lo, gx2, acc2, gx2_lo):
+                    gx1, acc1, gx1_lo, gx2, acc2, gx2_lo, partials=None):
         b = _lib.GnBwdDesc()
+        if partials is not None:     # reduction terms already accumulated by the dgrad conv (conv(..., gn_bwd=))
+            _chk(partials, torch.float32)
+            assert x2 is None and resample == 0 and partials.shape[:2] == (x1.shape[0], 32)
+            b.partials, b.partial_slots = _p(partials), partials.shape[2]
         b.f = self._gn_desc(x1, x2, gamma, beta, film, film_off, silu, resample, stats)
         b.dy = _p(_chk(dy, torch.float32))
         if gres is not None:

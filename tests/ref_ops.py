@@ -67,7 +67,8 @@ class RefOps:
         # mirror of CudaOps.conv_gn_slots: fusable in bf16 mode for group widths 8/16/32 (3 slots here)
         return 3 if (self.lo == torch.bfloat16 and Cout % groups == 0 and Cout // groups in (8, 16, 32)) else 0
 
-    def conv(self, a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None, gn_part=None):
+    def conv(self, a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None, gn_part=None,
+             gn_bwd=None):
         N, H, W, Cin = a.shape
         Cout = out.shape[3]
         kk = ksize * ksize
@@ -84,13 +85,39 @@ class RefOps:
         if accumulate:
             y = y + out.float()
         out.copy_(y.to(out.dtype))
-        if gn_part is not None:      # (sum, sum of squares) per (image, group): everything in slot 0, zeros elsewhere
+        if gn_part is not None and gn_bwd is None:
+            # (sum, sum of squares) per (image, group): everything in slot 0, zeros elsewhere
             G = gn_part.shape[1]
             yg = out.float().reshape(N, H * W, G, Cout // G)
             gn_part.zero_()
             gn_part[:, :, 0, 0] = yg.sum(dim=(1, 3))
             gn_part[:, :, 0, 1] = (yg * yg).sum(dim=(1, 3))
+        elif gn_part is not None:
+            gn_part.zero_()
+            t = self._gn_bwd_terms(out.float(), *gn_bwd)
+            gn_part[:, :, 0, 0], gn_part[:, :, 0, 1] = t[0], t[1]
         return out
+
+    @staticmethod
+    def _gn_bwd_terms(dy, x, gamma, beta, film, film_off, silu, stats):
+        """sum(dz g') and sum(dz g' xhat) per (image, 32 groups) of GroupNorm(+FiLM)(+SiLU) backward (NHWC tensors)."""
+        N, H, W, C = x.shape
+        ga, be = gamma.reshape(1, 1, 1, C), beta.reshape(1, 1, 1, C)
+        if film is not None:
+            sc = film[:, film_off:film_off + C].reshape(N, 1, 1, C)
+            sh = film[:, film_off + C:film_off + 2 * C].reshape(N, 1, 1, C)
+            ga, be = ga * (1 + sc), be * (1 + sc) + sh
+        mean = stats[..., 0].repeat_interleave(C // 32, dim=1).reshape(N, 1, 1, C)
+        rstd = stats[..., 1].repeat_interleave(C // 32, dim=1).reshape(N, 1, 1, C)
+        xhat = (x - mean) * rstd
+        d = dy
+        if silu:
+            z = xhat * ga + be
+            sg = torch.sigmoid(z)
+            d = d * (sg * (1 + z * (1 - sg)))
+        dzg = d * ga
+        g = lambda t: t.reshape(N, H * W, 32, C // 32).sum(dim=(1, 3))
+        return g(dzg), g(dzg * xhat)
 
     # ---- group norm ----
     @staticmethod
@@ -134,7 +161,12 @@ class RefOps:
         return y
 
     def gn_backward(self, x1, x2, gamma, beta, film, film_off, silu, resample, stats, dy, gres, gres_at_input,
-                    gx1, acc1, gx1_lo, gx2, acc2, gx2_lo):
+                    gx1, acc1, gx1_lo, gx2, acc2, gx2_lo, partials=None):
+        if partials is not None:     # the dgrad conv's reduction terms must describe THIS (x, dy) pair
+            assert x2 is None and resample == 0
+            t0, t1 = self._gn_bwd_terms(dy.float(), x1, gamma, beta, film, film_off, silu, stats)
+            for got, want in ((partials[..., 0].sum(-1), t0), (partials[..., 1].sum(-1), t1)):
+                assert torch.allclose(got, want, atol=1e-4 * float(want.abs().max()) + 1e-12, rtol=1e-3), "stale GN-backward partials"
         x = (x1 if x2 is None else torch.cat([x1, x2], dim=3)).detach().clone()
         xn = _nchw(x).contiguous().requires_grad_(True)
         with torch.enable_grad():

@@ -109,6 +109,54 @@ def test_groupnorm_forward_backward(ops, ref, case):
             assert rel_l2(res["cuda"][3].float(), res["ref"][3].float()) < 6e-3
 
 
+@pytest.mark.parametrize("N,H,Cin,C,k,film,silu,gres,acc,tune", [
+    (1, 64, 128, 256, 3, True, True, False, False, None),                      # ResBlock GN2 backward, direct epilogue
+    (1, 32, 256, 512, 3, True, True, False, False, {"block_n": 128, "split_k": 4}),   # cluster fold
+    (2, 8, 512, 1024, 3, False, True, True, True, None),                       # GN1 with skip gradient, accumulate
+    (1, 32, 1536, 512, 1, False, False, True, False, None),                    # attention norm (qkv dgrad), no SiLU
+    (3, 8, 256, 256, 1, True, True, True, False, {"block_n": 64, "split_k": 2}),
+])
+def test_gn_backward_fused_reduction(ops, N, H, Cin, C, k, film, silu, gres, acc, tune):
+    """dgrad conv with gn_bwd=... + gn_backward(partials=...) against the ordinary reduce + apply on the same dy."""
+    g = G(9)
+    dev = ops.device
+    a = torch.randn(N, H, H, Cin, generator=g).to(dev).to(torch.bfloat16)
+    w = (torch.randn(C, k * k * Cin, generator=g) / (k * k * Cin) ** 0.5).to(dev).to(torch.bfloat16)
+    x = torch.randn(N, H, H, C, generator=g).to(dev)
+    gamma, beta = torch.randn(C, generator=g).to(dev), torch.randn(C, generator=g).to(dev)
+    fm = (torch.randn(N, 2 * C + 64, generator=g) * 0.3).to(dev) if film else None
+    foff = 32 if film else 0
+    gr = torch.randn(N, H, H, C, generator=g).to(dev) if gres else None
+    slots = ops.conv_gn_slots(N, H, H, Cin, k, C) if tune is None else None
+    stats = torch.zeros(N, 32, 2, device=dev)
+    y = torch.empty(N, H, H, C, device=dev, dtype=torch.bfloat16)
+    ops.gn_forward(x, None, gamma, beta, fm, foff, silu, 0, stats, y)
+    res = []
+    for fused in (False, True):
+        dy = torch.empty(N, H, H, C, device=dev)
+        gx = torch.full((N, H, H, C), 0.25, device=dev)
+        gx_lo = torch.zeros(N, H, H, C, device=dev, dtype=torch.bfloat16)
+        part = None
+        if fused:
+            if slots is None:      # explicit tune: ask the library for this exact configuration
+                import ctypes as C_
+                from ishapediting_b200 import _lib
+                d = _lib.ConvDesc()
+                d.a, d.a_dtype, d.w, d.out, d.out_dtype = 256, _lib.BF16, 256, 256, _lib.F32
+                d.N, d.H, d.W, d.Cin, d.ksize, d.Cout, d.gn_cg = N, H, H, Cin, k, C, C // 32
+                d.block_n, d.split_k = tune.get("block_n", 0), tune.get("split_k", 0)
+                slots = int(ops.lib.isb_conv2d_gn_slots(C_.byref(d)))
+            assert slots > 0
+            part = torch.full((N, 32, slots, 2), float("nan"), device=dev)
+        ops.conv(a, w, None, k, dy, tune=tune, gn_part=part,
+                 gn_bwd=(x, gamma, beta, fm, foff, silu, stats) if fused else None)
+        ops.gn_backward(x, None, gamma, beta, fm, foff, silu, 0, stats, dy, gr, False, gx, acc, gx_lo, None, False, None,
+                        partials=part)
+        res.append((gx.clone(), gx_lo.float()))
+    assert rel_l2(res[1][0], res[0][0]) < 2e-5
+    assert rel_l2(res[1][1], res[0][1]) < 6e-3
+
+
 @pytest.mark.parametrize("lo", [torch.float32, torch.bfloat16], ids=["fp32_ffma", "bf16_mma"])
 @pytest.mark.parametrize("N,S,heads", [(1, 8, 2), (2, 16, 3), (1, 32, 4)])
 def test_attention_forward_backward(ops, ref, N, S, heads, lo):

@@ -86,7 +86,8 @@ def test_bf16_mode_emulation_within_tolerance():
     assert max(rel_l2(o.detach(), o_ref.detach()), rel_l2(f.detach(), f_ref.detach()), rel_l2(xd.grad, xr.grad)) < 2e-2
 
 
-def test_fused_gn_statistics_plan_mid_bf16():
+def test_fused_gn_statistics_plan_mid_bf16(monkeypatch):
+    monkeypatch.setenv("ISB_GN_FUSE_BWD", "1")     # the backward variant is off by default (measured slower)
     """NFD-width model in bf16 emulation: the plan routes GroupNorm statistics through the producer convs (RefOps
     asserts that every partials buffer a GroupNorm consumes describes exactly the tensor it normalises) and the
     result stays within the bf16 tolerance, twice in a row (stale buffers would show on the second pass)."""
@@ -101,10 +102,19 @@ def test_fused_gn_statistics_plan_mid_bf16():
             o_ref, f_ref = O.unet_forward(sd, cfg, inp, t, cfg["feat_layer"])
             o, f = model(inp, t, feat_layer=cfg["feat_layer"])
         assert max(rel_l2(o, o_ref), rel_l2(f, f_ref)) < 2e-2
-    plan = next(iter(model._plans.values())) if hasattr(model, "_plans") else None
-    if plan is not None:
-        fused = sum(1 for l in plan.layers if getattr(l, "h1_part", None) is not None or getattr(l, "x_part", None) is not None)
-        assert fused > 0
+    # backward: the dgrad convs deliver the GroupNorm-backward reduction terms (RefOps checks them the same way)
+    xr = x.clone().requires_grad_(True)
+    _, f_ref = O.unet_forward(sd, cfg, xr, t, cfg["feat_layer"])
+    proj = torch.randn(f_ref.shape, generator=g)
+    (f_ref * proj).sum().backward()
+    xd = x.clone().requires_grad_(True)
+    _, f = model(xd, t, feat_layer=cfg["feat_layer"])
+    (f * proj).sum().backward()
+    assert rel_l2(xd.grad, xr.grad) < 2e-2
+    plans = [p for p in model._plans.values()]
+    fused_fwd = sum(1 for p in plans for l in p.layers if getattr(l, "h1_part", None) is not None or getattr(l, "x_part", None) is not None)
+    fused_bwd = sum(1 for p in plans for l in p.layers if getattr(l, "b2_part", None) is not None or getattr(l, "b_part", None) is not None)
+    assert fused_fwd > 0 and fused_bwd > 0
 
 
 def test_diffusion_tables_and_respacing(small):
