@@ -250,24 +250,27 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: same step through host buffers (pinned), H2D of the step's inputs + D2H of its result ----
+    # HostStepPipeline (the product's host-buffer driver): step k+1's inputs travel while step k computes, step k's
+    # latent + loss travel back while step k+1 computes; the caller reads every step's result (one step late).
+    from ishapediting_b200.drag_utils import HostStepPipeline
+
     n_e2e = args.steps
     origin_host = [f.cpu().pin_memory() for f in ds.feature_guidance[:min(W_TIME, n_e2e)]]
     noise_host = torch.randn(1, 96, 128, 128).pin_memory()
-    img_host = torch.empty(1, 96, 128, 128).pin_memory()
-    loss_host = torch.empty(1).pin_memory()
-    origin_dev, noise_dev = torch.empty_like(ds.feature_guidance[0]), torch.empty(1, 96, 128, 128, device=dev)
-    h2d = origin_host[0].numel() * 4 + noise_host.numel() * 4
-    d2h = img_host.numel() * 4 + 4
+    pipe = HostStepPipeline(st)
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
+    checksum = 0.0
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
+    pipe.prefetch(0, origin_host[0], noise_host)
     for k in range(n_e2e):
-        origin_dev.copy_(origin_host[k % len(origin_host)], non_blocking=True)
-        noise_dev.copy_(noise_host, non_blocking=True)
-        st.step(step_index(k), origin_dev, noise_dev)
-        img_host.copy_(st.img, non_blocking=True)
-        loss_host.copy_(st.loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the step's result
+        if k + 1 < n_e2e:
+            pipe.prefetch(k + 1, origin_host[(k + 1) % len(origin_host)], noise_host)
+        pipe.run(k, step_index(k))
+        if k:
+            checksum += float(pipe.result(k - 1)[1])        # the caller reads the step's result
+    checksum += float(pipe.result(n_e2e - 1)[1])
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -379,7 +382,7 @@ def conv_roofline(st, ds, step_index, geo, feat_layer, use_graph, ms_full_step):
     orig = ops.conv
     rec = []
 
-    def count_conv(a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None):
+    def count_conv(a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None, **kw):
         M = a.shape[0] * a.shape[1] * a.shape[2]
         rec.append(2.0 * M * w.shape[0] * w.shape[1])
 

@@ -318,6 +318,72 @@ class GuidedStepper:
         self._graph.replay()
 
 
+class HostStepPipeline:
+    """Drives a GuidedStepper from HOST buffers (the shape of the reference's loop, drag_utils.py:341-385, where the
+    cached origin feature of every step lives in host memory and the latent is read back): the origin feature and
+    noise of step k+1 travel host->device on a copy stream while step k computes, and the new latent and loss of step
+    k travel device->host while step k+1 computes.  Every step still pays its copies; they just no longer sit on the
+    critical path.  Results are read one step late: result(k) blocks until step k's read-back has landed.
+
+        pipe.prefetch(0, origin_host, noise_host)
+        for k in range(n):
+            if k + 1 < n: pipe.prefetch(k + 1, next_origin_host, next_noise_host)
+            pipe.run(k, i_k)
+            if k: img, loss = pipe.result(k - 1)
+        img, loss = pipe.result(n - 1)
+    """
+
+    def __init__(self, stepper: "GuidedStepper"):
+        st = stepper
+        dev = st.img.device
+        assert dev.type == "cuda", "HostStepPipeline needs a CUDA stepper"
+        self.st = st
+        self.copy_in, self.copy_out = th.cuda.Stream(device=dev), th.cuda.Stream(device=dev)
+        two = range(2)
+        self.origin_dev = [th.empty_like(st.origin) for _ in two]
+        self.noise_dev = [th.empty_like(st.noise) for _ in two]
+        self.img_stage = [th.empty_like(st.img) for _ in two]
+        self.loss_stage = [th.empty_like(st.loss) for _ in two]
+        self.img_host = [th.empty(st.img.shape, dtype=st.img.dtype).pin_memory() for _ in two]
+        self.loss_host = [th.empty(st.loss.shape, dtype=st.loss.dtype).pin_memory() for _ in two]
+        ev = lambda: [th.cuda.Event() for _ in two]
+        self.in_ready, self.in_free, self.snap, self.out_done = ev(), ev(), ev(), ev()
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.origin_dev[0], self.noise_dev[0]))
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.img_stage[0], self.loss_stage[0]))
+
+    def prefetch(self, k, origin_host, noise_host):
+        """Start the host->device copy of step k's inputs (pinned host tensors)."""
+        s = k & 1
+        with th.cuda.stream(self.copy_in):
+            self.copy_in.wait_event(self.in_free[s])      # step k-2 has consumed this slot
+            self.origin_dev[s].copy_(origin_host, non_blocking=True)
+            self.noise_dev[s].copy_(noise_host, non_blocking=True)
+            self.in_ready[s].record(self.copy_in)
+
+    def run(self, k, i):
+        """Launch step k (respaced index i) on the current stream and start the read-back of its result."""
+        s = k & 1
+        main = th.cuda.current_stream()
+        main.wait_event(self.in_ready[s])
+        self.st.step(i, self.origin_dev[s], self.noise_dev[s])
+        self.in_free[s].record(main)
+        main.wait_event(self.out_done[s])                 # the read-back of step k-2 has left this staging slot
+        self.img_stage[s].copy_(self.st.img)              # snapshot: step k+1 updates st.img in place
+        self.loss_stage[s].copy_(self.st.loss)
+        self.snap[s].record(main)
+        with th.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(self.snap[s])
+            self.img_host[s].copy_(self.img_stage[s], non_blocking=True)
+            self.loss_host[s].copy_(self.loss_stage[s], non_blocking=True)
+            self.out_done[s].record(self.copy_out)
+
+    def result(self, k):
+        """(latent, loss) of step k in pinned host memory; valid until step k+2 is run."""
+        s = k & 1
+        self.out_done[s].synchronize()
+        return self.img_host[s], self.loss_host[s]
+
+
 # ------------------------------------------------------------------------------------------------------
 # DragStuff
 # ------------------------------------------------------------------------------------------------------

@@ -69,3 +69,45 @@ def test_guided_step_mid(mode):
                     sample=rel_l2(st.sample, ref["sample"]), loss=abs(float(st.loss) - float(ref["loss"])) / abs(float(ref["loss"])))
         print("guided", mode, use_graph, errs)
         assert max(errs.values()) < TOL[mode], (use_graph, errs)
+
+
+def test_host_step_pipeline_matches_sequential():
+    """HostStepPipeline (inputs prefetched / results read back on copy streams, one step late) must produce exactly
+    the latents and losses of the plain sequential loop over the same host inputs."""
+    from ishapediting_b200.drag_utils import DragGeometry, GuidedStepper, HostStepPipeline
+
+    cfg = O.mid_cfg()
+    sd = O.synth_state_dict(cfg)
+    model, diff = build_model(cfg, sd, "bf16", DEV)
+    sched = O.Schedule(cfg["diffusion_steps"], cfg["timestep_respacing"])
+    g, x, x2, noise = seeded_inputs(cfg)
+    origin, src, tgt, r1, voxel, pg, sg, masks = drag_problem(cfg, sd, sched, x2, noise, 49, g, r1=4, voxel=2.0 / 64)
+    geo = DragGeometry(src, tgt, r1, voxel, origin.shape[-1], origin.shape[1])
+    n = 6
+    origins = [(origin.permute(0, 2, 3, 1).contiguous() * (1.0 + 0.05 * k)).pin_memory() for k in range(n)]
+    noises = [torch.randn(noise.shape, generator=g).pin_memory() for _ in range(n)]
+    st = GuidedStepper(model, diff, geo, cfg["feat_layer"], 0.2, "l2", 600.0, use_graph=True)
+    for _ in range(2):                                   # warm-up + capture
+        st.img.copy_(x.to(DEV))
+        st.step(49, origins[0].to(DEV), noises[0].to(DEV))
+    st.img.copy_(x.to(DEV))
+    seq = []
+    for k in range(n):
+        st.step(49 - k, origins[k].to(DEV), noises[k].to(DEV))
+        seq.append((st.img.cpu().clone(), st.loss.cpu().clone()))
+    st.img.copy_(x.to(DEV))
+    pipe = HostStepPipeline(st)
+    got = []
+    pipe.prefetch(0, origins[0], noises[0])
+    for k in range(n):
+        if k + 1 < n:
+            pipe.prefetch(k + 1, origins[k + 1], noises[k + 1])
+        pipe.run(k, 49 - k)
+        if k:
+            r = pipe.result(k - 1)
+            got.append((r[0].clone(), r[1].clone()))
+    r = pipe.result(n - 1)
+    got.append((r[0].clone(), r[1].clone()))
+    for k in range(n):
+        assert torch.equal(got[k][0], seq[k][0]), k
+        assert torch.equal(got[k][1], seq[k][1]), k
