@@ -6,9 +6,10 @@
 // backward pass — ~1.3 ms of the 5.7 ms guided step.  Here the probabilities never leave the SM:
 //   forward     one CTA per (64 queries, head): S = QK^T -> online softmax -> O += PV; writes O and the
 //               per-row log-sum-exp (log2 domain)
-//   backward 1  one CTA per (64 queries, head): recomputes P from the log-sum-exp, dP = dO V^T,
+//   backward    ONE launch, two kinds of CTA:
+//     dq half   one CTA per (64 queries, head): recomputes P from the log-sum-exp, dP = dO V^T,
 //               dS = P o (dP - delta) * scale, dQ += dS K;  also writes delta = rowsum(dO o O)
-//   backward 2  one CTA per (64 keys, head): recomputes P^T, dV += P^T dO, dK += dS^T Q
+//     dkv half  one CTA per (64 keys, head): recomputes P^T (and delta), dV += P^T dO, dK += dS^T Q
 // No atomics: every output element has exactly one writer and a fixed summation order (deterministic).
 // Tensor cores through mma.sync m16n8k16 (bf16 in, fp32 accumulate), operands staged with cp.async into padded
 // shared-memory tiles and fetched with ldmatrix.  (The GEMMs here are 64-deep and ~40 GFLOP per step in total:
@@ -222,18 +223,40 @@ fa_fwd_kernel(const FaParams p) {
   }
 }
 
+// delta[row] = sum_c dO[row][c] * O[row][c] for the 64 rows of a tile: two threads per row, 32 channels each
+__device__ __forceinline__ void fa_delta_fetch(const __nv_bfloat16* dO, const __nv_bfloat16* O, size_t C, int tid,
+                                               uint4 (&ua)[4], uint4 (&ub)[4]) {
+  const int row = tid >> 1, half = tid & 1;
+  const uint4* a = reinterpret_cast<const uint4*>(dO + static_cast<size_t>(row) * C + half * 32);
+  const uint4* b = reinterpret_cast<const uint4*>(O + static_cast<size_t>(row) * C + half * 32);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ua[i] = a[i];
+    ub[i] = b[i];
+  }
+}
+__device__ __forceinline__ float fa_delta_dot(const uint4 (&ua)[4], const uint4 (&ub)[4]) {
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162* pa2 = reinterpret_cast<const __nv_bfloat162*>(&ua[i]);
+    const __nv_bfloat162* pb2 = reinterpret_cast<const __nv_bfloat162*>(&ub[i]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __bfloat1622float2(pa2[e]), fb = __bfloat1622float2(pb2[e]);
+      acc = fmaf(fa.x, fb.x, acc);
+      acc = fmaf(fa.y, fb.y, acc);
+    }
+  }
+  return acc + __shfl_xor_sync(0xffffffffu, acc, 1);
+}
+
 // ---- backward 1: dQ (and delta) ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-fa_bwd_dq_kernel(const FaParams p) {
-  pdl_trigger();
-  pdl_wait();
-  extern __shared__ __align__(16) uint8_t fa_smem[];
-  __shared__ float Dsm[FA_B];
+__device__ __forceinline__ void fa_bwd_dq_body(const FaParams& p, uint8_t* fa_smem, float* Dsm, int qb, int h, int n) {
   const uint32_t sQ = fa_smem_u32(fa_smem), sdO = sQ + FA_TILE;
   auto sK = [&](int j) { return sQ + static_cast<uint32_t>((2 + 2 * (j & 1)) * FA_TILE); };
   auto sV = [&](int j) { return sQ + static_cast<uint32_t>((3 + 2 * (j & 1)) * FA_TILE); };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2;
-  const int qb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const size_t C3 = static_cast<size_t>(3) * p.heads * FA_D, C = static_cast<size_t>(p.heads) * FA_D;
   const __nv_bfloat16* base = p.qkv + static_cast<size_t>(n) * p.T * C3 + static_cast<size_t>(h) * 3 * FA_D;
   const int row0 = qb * FA_B;
@@ -246,26 +269,12 @@ fa_bwd_dq_kernel(const FaParams p) {
   cp_async_commit();
   const size_t stat0 = (static_cast<size_t>(n) * p.heads + h) * p.T + row0;
   {  // delta[row] = sum_c dO[row][c] * O[row][c]: two threads per row
-    const int row = tid >> 1, half = tid & 1;
-    const uint4* a = reinterpret_cast<const uint4*>(dO + static_cast<size_t>(row) * C + half * 32);
-    const uint4* b = reinterpret_cast<const uint4*>(O + static_cast<size_t>(row) * C + half * 32);
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 ua = a[i], ub = b[i];
-      const __nv_bfloat162* pa2 = reinterpret_cast<const __nv_bfloat162*>(&ua);
-      const __nv_bfloat162* pb2 = reinterpret_cast<const __nv_bfloat162*>(&ub);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 fa = __bfloat1622float2(pa2[e]), fb = __bfloat1622float2(pb2[e]);
-        acc = fmaf(fa.x, fb.x, acc);
-        acc = fmaf(fa.y, fb.y, acc);
-      }
-    }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (half == 0) {
-      Dsm[row] = acc;
-      p.delta[stat0 + row] = acc;
+    uint4 ua[4], ub[4];
+    fa_delta_fetch(dO, O, C, tid, ua, ub);
+    const float acc = fa_delta_dot(ua, ub);
+    if ((tid & 1) == 0) {
+      Dsm[tid >> 1] = acc;
+      p.delta[stat0 + (tid >> 1)] = acc;
     }
   }
   const float L0 = p.lse[stat0 + warp * 16 + g], L1 = p.lse[stat0 + warp * 16 + g + 8];
@@ -311,20 +320,16 @@ fa_bwd_dq_kernel(const FaParams p) {
 }
 
 // ---- backward 2: dK, dV ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-fa_bwd_dkv_kernel(const FaParams p) {
-  pdl_trigger();
-  pdl_wait();
-  extern __shared__ __align__(16) uint8_t fa_smem[];
-  __shared__ float Ls[2][FA_B], Ds[2][FA_B];
+__device__ __forceinline__ void fa_bwd_dkv_body(const FaParams& p, uint8_t* fa_smem, float (*Ls)[FA_B], float (*Ds)[FA_B],
+                                                int kb, int h, int n) {
   const uint32_t sK = fa_smem_u32(fa_smem), sV = sK + FA_TILE;
   auto sQ = [&](int i) { return sK + static_cast<uint32_t>((2 + 2 * (i & 1)) * FA_TILE); };
   auto sdO = [&](int i) { return sK + static_cast<uint32_t>((3 + 2 * (i & 1)) * FA_TILE); };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, t = lane & 3;
-  const int kb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const size_t C3 = static_cast<size_t>(3) * p.heads * FA_D, C = static_cast<size_t>(p.heads) * FA_D;
   const __nv_bfloat16* base = p.qkv + static_cast<size_t>(n) * p.T * C3 + static_cast<size_t>(h) * 3 * FA_D;
   const __nv_bfloat16* dO = p.d_out + static_cast<size_t>(n) * p.T * C + static_cast<size_t>(h) * FA_D;
+  const __nv_bfloat16* O = p.out + static_cast<size_t>(n) * p.T * C + static_cast<size_t>(h) * FA_D;
   const size_t stat0 = (static_cast<size_t>(n) * p.heads + h) * p.T;
   const int key0 = kb * FA_B;
   fa_load_tile(sK, base + static_cast<size_t>(key0) * C3 + FA_D, C3, tid);
@@ -332,8 +337,15 @@ fa_bwd_dkv_kernel(const FaParams p) {
   fa_load_tile(sQ(0), base, C3, tid);
   fa_load_tile(sdO(0), dO, C, tid);
   cp_async_commit();
+  // delta = rowsum(dO o O) is recomputed here for every query block (the dq half of the launch runs concurrently
+  // and cannot hand it over): the 64 rows are fetched into registers one iteration ahead
+  uint4 ua[4], ub[4];
+  fa_delta_fetch(dO, O, C, tid, ua, ub);
   if (tid < FA_B) Ls[0][tid] = p.lse[stat0 + tid];
-  else Ds[0][tid - FA_B] = p.delta[stat0 + tid - FA_B];
+  {
+    const float d = fa_delta_dot(ua, ub);
+    if ((tid & 1) == 0) Ds[0][tid >> 1] = d;
+  }
   const int nq = p.T / FA_B;
   float dk[8][4], dv[8][4];
   fa_zero(dk);
@@ -345,7 +357,7 @@ fa_bwd_dkv_kernel(const FaParams p) {
       fa_load_tile(sQ((i + 1) & 1), base + r * C3, C3, tid);
       fa_load_tile(sdO((i + 1) & 1), dO + r * C, C, tid);
       if (tid < FA_B) Ls[(i + 1) & 1][tid] = p.lse[stat0 + r + tid];
-      else Ds[(i + 1) & 1][tid - FA_B] = p.delta[stat0 + r + tid - FA_B];
+      fa_delta_fetch(dO + r * C, O + r * C, C, tid, ua, ub);
     }
     cp_async_commit();
     cp_async_wait<1>();
@@ -378,6 +390,10 @@ fa_bwd_dkv_kernel(const FaParams p) {
     fa_gemm_nn(dv, pa, sdO(i & 1), lane);
     fa_pack_a(pa, dpt);
     fa_gemm_nn(dk, pa, sQ(i & 1), lane);
+    if (i + 1 < nq) {      // the rows fetched at the top of this iteration have arrived by now
+      const float d = fa_delta_dot(ua, ub);
+      if ((tid & 1) == 0) Ds[(i + 1) & 1][tid >> 1] = d;
+    }
     __syncthreads();
   }
   __nv_bfloat16* dst = p.d_qkv + (static_cast<size_t>(n) * p.T + key0) * C3 + static_cast<size_t>(h) * 3 * FA_D;
@@ -385,13 +401,28 @@ fa_bwd_dkv_kernel(const FaParams p) {
   fa_store_rows(dst + 2 * FA_D, C3, dv, warp, lane, 1.0f, 1.0f);
 }
 
+// One launch for the whole backward: the first T/64 CTAs of a (head, image) take the key blocks (dK, dV: four
+// GEMMs per tile pair, the longer job, scheduled first), the other T/64 the query blocks (dQ).  The two halves share
+// nothing but inputs, so they fill twice as many SMs as either kernel alone (128 CTAs of 4 warps each at T = 1024
+// left most of the machine idle) and one launch latency disappears.
+__global__ void __launch_bounds__(128)
+fa_bwd_kernel(const FaParams p) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t fa_smem[];
+  __shared__ float stat_sm[4][FA_B];
+  const int nblk = p.T / FA_B;
+  const int h = blockIdx.y, n = blockIdx.z;
+  if (static_cast<int>(blockIdx.x) < nblk) fa_bwd_dkv_body(p, fa_smem, &stat_sm[0], &stat_sm[2], blockIdx.x, h, n);
+  else fa_bwd_dq_body(p, fa_smem, stat_sm[0], static_cast<int>(blockIdx.x) - nblk, h, n);
+}
+
 constexpr int FA_SMEM_FWD = 5 * FA_TILE;   // 46080
 constexpr int FA_SMEM_BWD = 6 * FA_TILE;   // 55296
 
 int attention_flash_init() {
   ISB_CUDA(cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FWD));
-  ISB_CUDA(cudaFuncSetAttribute(fa_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BWD));
-  ISB_CUDA(cudaFuncSetAttribute(fa_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BWD));
+  ISB_CUDA(cudaFuncSetAttribute(fa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BWD));
   return ISB_OK;
 }
 
@@ -442,11 +473,9 @@ int isb_attention_flash_backward(const void* qkv, const void* out, const void* d
   p.heads = heads;
   p.scale = 1.0f / sqrtf(static_cast<float>(ch));
   p.scale_log2 = p.scale * 1.4426950408889634f;
-  const dim3 grid(T / isb::FA_B, heads, N);
+  const dim3 grid(2 * (T / isb::FA_B), heads, N);
   isb::PdlFamily fam(3);
-  ISB_CUDA(isb::launch(isb::fa_bwd_dq_kernel, grid, dim3(128), isb::FA_SMEM_BWD, isb::as_stream(stream), p));
-  ISB_LAUNCH_CHECK();
-  ISB_CUDA(isb::launch(isb::fa_bwd_dkv_kernel, grid, dim3(128), isb::FA_SMEM_BWD, isb::as_stream(stream), p));
+  ISB_CUDA(isb::launch(isb::fa_bwd_kernel, grid, dim3(128), isb::FA_SMEM_BWD, isb::as_stream(stream), p));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }
