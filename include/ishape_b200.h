@@ -92,6 +92,9 @@ typedef struct isb_conv_desc {
   int w_tiled;           /* 1: w is panel-tiled (see above); needs Cout % 64 == 0 */
   int two_cta;           /* 0 heuristic, 1 force the CTA-pair (cta_group::2) kernel, 2 forbid it */
   int debug_flags;       /* profiling only (results become garbage): bit0 skip the TMA loads, bit1 skip the MMAs */
+  int min_smem_bytes;    /* 0, or a floor for the dynamic shared memory of the launch: a background-stream conv asks
+                            for > half an SM (e.g. 116 KB) so that only one of its CTAs is resident per SM and the
+                            latency-critical stream's CTAs always find room beside it */
   /* Optional GroupNorm statistics of the OUTPUT, fused into the epilogue (bf16 path, fp32 out): every CTA writes
    * the (sum, sum of squares) of its part of each group of gn_cg consecutive output channels; the consumer
    * (isb_gn_forward with `partials`) folds the gn_slots contributions per (image, group) in fixed order.

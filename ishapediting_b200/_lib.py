@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
         ("w", c_void_p), ("bias", c_void_p), ("residual", c_void_p),
         ("out", c_void_p), ("out_dtype", c_int), ("Cout", c_int),
         ("accumulate", c_int),
-        ("block_n", c_int), ("split_k", c_int), ("stages", c_int), ("w_tiled", c_int), ("two_cta", c_int), ("debug_flags", c_int),
+        ("block_n", c_int), ("split_k", c_int), ("stages", c_int), ("w_tiled", c_int), ("two_cta", c_int), ("debug_flags", c_int), ("min_smem_bytes", c_int),
         ("gn_partials", c_void_p), ("gn_cg", c_int), ("gn_slots", c_int),
         ("gn_mode", c_int), ("gb_x", c_void_p), ("gb_gamma", c_void_p), ("gb_beta", c_void_p),
         ("gb_film", c_void_p), ("gb_film_stride", c_int), ("gb_stats", c_void_p), ("gb_silu", c_int),

@@ -1204,6 +1204,7 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   p.stages = stages;
   plan->smem_bytes = stages * stage_bytes;
   plan->smem_bytes += 1024;
+  if (d->min_smem_bytes > plan->smem_bytes) plan->smem_bytes = d->min_smem_bytes < TC_SMEM_LIMIT ? d->min_smem_bytes : TC_SMEM_LIMIT;
   plan->counter_bytes = (static_cast<size_t>(mtiles) * ntiles * sizeof(int) + 255) & ~static_cast<size_t>(255);
   // split-K partial tiles [tile][split][128][bn] fp32 behind the arrival counters (the cluster path does not use
   // the counters); re-written by every launch, so they live in L2

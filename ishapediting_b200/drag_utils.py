@@ -219,9 +219,14 @@ class GuidedStepper:
         self.use_graph = use_graph and dev.type == "cuda"
         self.overlap_tail = overlap_tail
         if dev.type == "cuda":
-            self._side = th.cuda.Stream(device=dev)
+            # The forward tail is off the critical path: it gets the LOW priority (0), the captured main stream and
+            # the backward side stream the HIGH one, so that whenever an SM frees a slot the block scheduler hands it
+            # to the backward chain first (ISB_STREAM_PRIO=0 puts everything back on equal footing).
+            hi = -1 if os.environ.get("ISB_STREAM_PRIO", "1") != "0" else 0
+            self._side = th.cuda.Stream(device=dev, priority=0)
+            self._cap_stream = th.cuda.Stream(device=dev, priority=hi)
             self._ev_fork, self._ev_join = th.cuda.Event(), th.cuda.Event()
-            self._side_bwd = (th.cuda.Stream(device=dev), th.cuda.Event(), th.cuda.Event())
+            self._side_bwd = (th.cuda.Stream(device=dev, priority=hi), th.cuda.Event(), th.cuda.Event())
         self._film = {}
         self._film_cache = os.environ.get("ISB_FILM_CACHE", "1") != "0"
         self._bwd_branches = os.environ.get("ISB_SIDE_BWD", "1") != "0"
@@ -264,9 +269,11 @@ class GuidedStepper:
             # of small, latency-bound kernels.  Run the two concurrently and join before the update.
             main = th.cuda.current_stream()
             self._ev_fork.record(main)
-            with th.cuda.stream(self._side), ops.workspace_slot(1):
+            bg = os.environ.get("ISB_TAIL_BG", "0") == "1"    # measured neutral on B200 (profiles/README.md): off
+            with th.cuda.stream(self._side), ops.workspace_slot(1), ops.background(bg):
                 self._side.wait_event(self._ev_fork)
-                plan.forward_tail()
+                if os.environ.get("ISB_DEBUG_SKIP_TAIL", "0") != "1":   # timing experiment only (wrong results)
+                    plan.forward_tail()
                 self._ev_join.record(self._side)
         for b in range(self.batch):           # the drag loss couples nothing across edits: one small launch set each
             geo = self.geos[b]
@@ -311,7 +318,7 @@ class GuidedStepper:
                 return
             img_keep = self.img.clone()
             g = th.cuda.CUDAGraph()
-            with th.cuda.graph(g):
+            with th.cuda.graph(g, stream=self._cap_stream):
                 self._body()
             self._graph = g
             self.img.copy_(img_keep)    # capture does not execute; restore and replay for real

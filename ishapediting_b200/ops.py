@@ -60,6 +60,7 @@ class CudaOps:
         self.tile_weights = os.environ.get("ISB_TILED_WEIGHTS", "0") == "1"
         self._ws = {}
         self._ws_slot = 0
+        self._bg = False
         self._gn_scratch = {}
 
     # ---- memory -----------------------------------------------------------
@@ -93,6 +94,17 @@ class CudaOps:
             yield
         finally:
             self._ws_slot = prev
+
+    @contextlib.contextmanager
+    def background(self, on=True):
+        """Convolutions launched inside this context belong to work that runs BESIDE a latency-critical stream (the
+        forward tail next to the backward pass): they ask for more than half an SM's shared memory, so only one of
+        their CTAs is resident per SM and the critical stream's CTAs always find room next to it."""
+        prev, self._bg = self._bg, on
+        try:
+            yield
+        finally:
+            self._bg = prev
 
     def _scratch(self, N, groups=32, which="fwd"):
         """GroupNorm reduction scratch (arrival counters + partials).  Forward and backward kernels get
@@ -192,6 +204,8 @@ class CudaOps:
             d.block_n, d.split_k, d.stages = tune.get("block_n", 0), tune.get("split_k", 0), tune.get("stages", 0)
             d.two_cta = tune.get("two_cta", 0)
             d.debug_flags = tune.get("debug", 0)
+        if self._bg:
+            d.min_smem_bytes = 116 * 1024
         if gn_part is not None:
             _chk(gn_part, torch.float32)
             assert gn_part.shape[0] == N and gn_part.shape[3] == 2 and d.Cout % gn_part.shape[1] == 0

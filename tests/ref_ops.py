@@ -28,6 +28,10 @@ class RefOps:
     def workspace_slot(self, slot):
         yield
 
+    @contextlib.contextmanager
+    def background(self, on=True):
+        yield
+
     def __init__(self, mode="fp32", device="cpu"):
         self.mode = mode
         self.lo = torch.bfloat16 if mode == "bf16" else torch.float32
