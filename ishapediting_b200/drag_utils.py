@@ -272,8 +272,7 @@ class GuidedStepper:
             bg = os.environ.get("ISB_TAIL_BG", "0") == "1"    # measured neutral on B200 (profiles/README.md): off
             with th.cuda.stream(self._side), ops.workspace_slot(1), ops.background(bg):
                 self._side.wait_event(self._ev_fork)
-                if os.environ.get("ISB_DEBUG_SKIP_TAIL", "0") != "1":   # timing experiment only (wrong results)
-                    plan.forward_tail()
+                plan.forward_tail()
                 self._ev_join.record(self._side)
         for b in range(self.batch):           # the drag loss couples nothing across edits: one small launch set each
             geo = self.geos[b]
