@@ -25,8 +25,8 @@ struct BgemmParams {
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(256)
 bgemm_kernel(const BgemmParams p) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ __align__(16) float As[BG_BK][BG_BM + BG_PAD];
   __shared__ __align__(16) float Bs[BG_BK][BG_BN + BG_PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -151,8 +151,8 @@ __device__ __forceinline__ void tg_stash(const float* r, __nv_bfloat16 (*sm)[TG_
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(128)
 bgemm_mma_kernel(const BgemmParams p) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ __align__(16) __nv_bfloat16 As[TG_BM][TG_LD];
   __shared__ __align__(16) __nv_bfloat16 Bs[TG_BN][TG_LD];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -248,8 +248,8 @@ static int bgemm_any(const BgemmParams& p, int batches, bool tensor_cores, cudaS
 // one block (128 threads) per row of length T: in-place fp32 softmax (unet.py:352)
 __global__ void __launch_bounds__(128)
 softmax_rows_kernel(float* __restrict__ s, int T) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ float red[4];
   float* row = s + static_cast<size_t>(blockIdx.x) * T;
   const int tid = threadIdx.x;
@@ -289,8 +289,8 @@ softmax_rows_kernel(float* __restrict__ s, int T) {
 // dS = alpha * P * (dP - sum_s dP*P), in place on dp
 __global__ void __launch_bounds__(128)
 softmax_bwd_rows_kernel(const float* __restrict__ probs, float* __restrict__ dp, int T, float alpha) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ float red[4];
   const float* prow = probs + static_cast<size_t>(blockIdx.x) * T;
   float* drow = dp + static_cast<size_t>(blockIdx.x) * T;

@@ -144,8 +144,8 @@ __device__ __forceinline__ void fa_store_rows(__nv_bfloat16* dst, size_t row_str
 // ---- forward -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 fa_fwd_kernel(const FaParams p) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   extern __shared__ __align__(16) uint8_t fa_smem[];
   const uint32_t sQ = fa_smem_u32(fa_smem);
   auto sK = [&](int j) { return sQ + static_cast<uint32_t>((1 + 2 * (j & 1)) * FA_TILE); };
@@ -407,8 +407,8 @@ __device__ __forceinline__ void fa_bwd_dkv_body(const FaParams& p, uint8_t* fa_s
 // left most of the machine idle) and one launch latency disappears.
 __global__ void __launch_bounds__(128)
 fa_bwd_kernel(const FaParams p) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   extern __shared__ __align__(16) uint8_t fa_smem[];
   __shared__ float stat_sm[4][FA_B];
   const int nblk = p.T / FA_B;

@@ -21,8 +21,8 @@ struct SimtParams {
 
 __global__ void __launch_bounds__(256)
 conv_simt_kernel(const SimtParams p) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ float As[SM_BK][SM_BM + SM_PAD];
   __shared__ float Bs[SM_BK][SM_BN + SM_PAD];
   const int tid = threadIdx.x;

@@ -20,8 +20,8 @@ struct DdpmArgs {
 // block: 32 pixels x 32 channels; grid (HW/32, C/32, N)
 __global__ void __launch_bounds__(256)
 ddpm_step_kernel(const DdpmArgs a) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ float t_eps[32][33];
   __shared__ float t_v[32][33];
   const int n = blockIdx.z;

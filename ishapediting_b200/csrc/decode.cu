@@ -114,8 +114,8 @@ __device__ __forceinline__ void mlp_layer(const float (*W)[DC_LD], const float* 
 template <bool GRID>
 __global__ void __launch_bounds__(DC_THREADS, 1)
 triplane_decode_kernel(const DecodeArgs a) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   extern __shared__ __align__(16) uint8_t dsm_raw[];
   DecodeSmem& s = *reinterpret_cast<DecodeSmem*>(dsm_raw);
   const int tid = threadIdx.x;

@@ -51,8 +51,8 @@ __device__ __forceinline__ Bilin bilin_setup(float gx, float gy, int S) {
 // grid (npts, 3); block loops over the Ca aligned channels
 __global__ void __launch_bounds__(192)
 drag_sample_kernel(const DragArgs a) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   const int j = blockIdx.x, pl = blockIdx.y;
   const int S = a.S;
   const size_t pj = static_cast<size_t>(pl) * a.npts + j;
@@ -111,8 +111,8 @@ constexpr int DG_MAXLIST = 1024;
 
 __global__ void __launch_bounds__(DG_THREADS)
 drag_gather_kernel(const DragArgs a) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ int s_j[DG_MAXLIST];
   __shared__ float s_w[DG_MAXLIST];
   __shared__ int s_cnt[DG_THREADS / 32 + 1];
@@ -216,8 +216,8 @@ drag_gather_kernel(const DragArgs a) {
 
 __global__ void __launch_bounds__(256)
 drag_loss_kernel(const DragArgs a) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ double red[2][8];
   double motion = 0, mask = 0;
   const int n_motion = 3 * a.npts;
@@ -241,8 +241,8 @@ drag_loss_kernel(const DragArgs a) {
 __global__ void __launch_bounds__(256)
 resize_feat_align_kernel(const float* __restrict__ feat, int S, int Cf, const int32_t* __restrict__ chan_map,
                          float* __restrict__ out, int Ca) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = 3LL * S * S * Ca;
   if (idx >= total) return;

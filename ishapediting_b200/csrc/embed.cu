@@ -10,8 +10,8 @@ namespace isb {
 // (computed with the reference's own expression so the table is bit-identical).
 __global__ void sinusoid_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs, int N, int half,
                                 float* __restrict__ emb) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * half) return;
   const int n = idx / half, i = idx % half;
@@ -24,8 +24,8 @@ __global__ void sinusoid_kernel(const int64_t* __restrict__ t, const float* __re
 __global__ void __launch_bounds__(256)
 gemv_rows_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ in,
                  float* __restrict__ out, int R, int K, int N, int silu_out) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
   const int lane = threadIdx.x & 31;

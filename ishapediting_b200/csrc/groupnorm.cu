@@ -88,8 +88,8 @@ __device__ __forceinline__ bool gn_block_reduce_and_fold(const GnArgs& a, int ng
 // grid (splits, G, N)
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const GnArgs a) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   const int split = blockIdx.x, g = blockIdx.y, n = blockIdx.z;
   const int V = a.Cg / 8;
   const long long total = static_cast<long long>(a.HW) * V;
@@ -183,8 +183,8 @@ __device__ __forceinline__ void gn_apply_one(const GnArgs& a, const GnFwdOut& o,
 
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const GnArgs a, const GnFwdOut o) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   const int CV = a.C / 8;
   const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;  // thread grid
   const long long total = static_cast<long long>(a.N) * Ho * Wo * CV;
@@ -208,8 +208,8 @@ gn_apply_kernel(const GnArgs a, const GnFwdOut o) {
 constexpr int GN_PART_UNROLL = 4;
 __global__ void __launch_bounds__(256)
 gn_apply_part_kernel(const GnArgs a, const GnFwdOut o, const float2* __restrict__ partials, int slots, int ppc) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ double2 runs[32];
   __shared__ float s_mean[4], s_rstd[4];
   const int tid = threadIdx.x;
@@ -333,8 +333,8 @@ __device__ __forceinline__ void gn_cluster_fold(double* s_part, double& t0, doub
 // (the second read of the group's slice hits L1/L2).  Saves a launch and the global round trip.
 __global__ void __launch_bounds__(512)
 gn_fused_fwd_kernel(const GnArgs a, const GnFwdOut o) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ double sh0[16], sh1[16];
   __shared__ double s_part[2];
   __shared__ float s_mean, s_rstd;
@@ -436,8 +436,8 @@ __device__ __forceinline__ void gn_bwd_terms8(const GnArgs& a, const GnBwdArgs& 
 
 __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const GnArgs a, const GnBwdArgs b) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   const int split = blockIdx.x, g = blockIdx.y, n = blockIdx.z;
   const int V = a.Cg / 8;
   const long long total = static_cast<long long>(a.HW) * V;
@@ -490,8 +490,8 @@ __device__ __forceinline__ void gn_bwd_apply_one(const GnArgs& a, const GnBwdArg
 
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const GnArgs a, const GnBwdArgs b) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   const int CV = a.C / 8;
   const long long total = static_cast<long long>(a.N) * a.HW * CV;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -527,8 +527,8 @@ __device__ __forceinline__ void gn_row_bwd_terms(const GnArgs& a, const GnRowBwd
 constexpr int GN_PART_UNROLL_BWD = 2;
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_part_kernel(const GnArgs a, const GnBwdArgs b, const float2* __restrict__ partials, int slots, int ppc) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ double2 runs[32];
   __shared__ float s_m1[4], s_m2[4];
   const int tid = threadIdx.x;
@@ -617,8 +617,8 @@ gn_bwd_apply_part_kernel(const GnArgs a, const GnBwdArgs b, const float2* __rest
 // single-launch backward for small tensors (see gn_fused_fwd_kernel)
 __global__ void __launch_bounds__(512)
 gn_fused_bwd_kernel(const GnArgs a, const GnBwdArgs b) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // predecessor complete and flushed
+  pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   __shared__ double sh0[16], sh1[16];
   __shared__ double s_part[2];
   __shared__ float s_m1, s_m2;

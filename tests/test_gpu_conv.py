@@ -95,3 +95,19 @@ def test_conv_fused_groupnorm_statistics(ops_by_mode, case):
     assert (sts[0][..., 0] - sts[1][..., 0]).abs().max() < 1e-5
     assert ((sts[0][..., 1] - sts[1][..., 1]).abs() / sts[0][..., 1]).max() < 1e-5
     assert (ys[0] - ys[1]).abs().max() < 0.05      # bf16 outputs: at most a rounding flip
+
+
+def test_conv_background_occupancy_limit(ops_by_mode):
+    """ops.background(): the same convolution with the one-CTA-per-SM shared-memory floor gives the same bits."""
+    ops = ops_by_mode["bf16"]
+    dev = ops.device
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(1, 64, 64, 128, generator=g).to(dev).to(torch.bfloat16)
+    w = (torch.randn(256, 9 * 128, generator=g) / 34.0).to(dev).to(torch.bfloat16)
+    bias = torch.randn(256, generator=g).to(dev)
+    o1, o2 = torch.empty(1, 64, 64, 256, device=dev), torch.empty(1, 64, 64, 256, device=dev)
+    ops.conv(a, w, bias, 3, o1)
+    with ops.background():
+        ops.conv(a, w, bias, 3, o2)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2)
