@@ -312,6 +312,9 @@ uint64_t isb_launch_count(void);
 /* Profiling only (tools/trace_conv.py): conv launches made with isb_conv_desc.debug_flags bit 2 write per-CTA
  * %globaltimer phase stamps ([cta][16] uint64 + a per-iteration area, 4096*16*8 bytes) to this device buffer. */
 void isb_debug_set_trace(void* device_buffer);
+/* Profiling only (tools/launch_floor.py): enqueue n dependent empty kernels (ctas x threads), optionally as
+ * programmatic dependents — measures the floor of one dependent launch inside a stream / CUDA graph. */
+int isb_debug_launch_chain(int n, int ctas, int threads, int pdl, isb_stream_t stream);
 
 #ifdef __cplusplus
 }

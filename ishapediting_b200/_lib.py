@@ -108,6 +108,7 @@ PROTOTYPES = {
     "isb_last_error": (C.c_char_p, []),
     "isb_launch_count": (C.c_uint64, []),
     "isb_debug_set_trace": (None, [c_void_p]),
+    "isb_debug_launch_chain": (c_int, [c_int, c_int, c_int, c_int, c_void_p]),
     "isb_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "isb_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "isb_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -49,6 +49,29 @@ void conv_tc_set_trace(void* ptr);
 int decode_init();      // decode.cu
 int attention_flash_init();   // attention_flash.cu
 
+// profiling only: a chain of n dependent, (almost) empty kernels — the floor of one dependent launch in a stream /
+// graph, with and without programmatic dependent launch (tools/launch_floor.py)
+__global__ void debug_chain_kernel(float* p) {
+  pdl_wait();
+  pdl_trigger();
+  if (p != nullptr && threadIdx.x == 0 && blockIdx.x == 0) p[0] += 1.0f;
+}
+int debug_launch_chain(int n, int ctas, int threads, int pdl, cudaStream_t st) {
+  for (int i = 0; i < n; ++i) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    ISB_CUDA(cudaLaunchKernelEx(&cfg, debug_chain_kernel, static_cast<float*>(nullptr)));
+  }
+  return ISB_OK;
+}
+
 }  // namespace isb
 
 extern "C" {
@@ -60,6 +83,10 @@ const char* isb_last_error(void) { return isb::t_err; }
 uint64_t isb_launch_count(void) { return isb::g_launches.load(); }
 
 void isb_debug_set_trace(void* device_buffer) { isb::conv_tc_set_trace(device_buffer); }
+
+int isb_debug_launch_chain(int n, int ctas, int threads, int pdl, isb_stream_t stream) {
+  return isb::debug_launch_chain(n, ctas, threads, pdl, isb::as_stream(stream));
+}
 
 int isb_init(int device) {
   std::lock_guard<std::mutex> lk(isb::g_mu);
