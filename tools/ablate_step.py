@@ -34,7 +34,9 @@ def time_stepper(st, origin, reps=20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", default="bf16")
+    ap.add_argument("--batch", type=int, default=1, help="edits advanced together (throughput mode)")
     args = ap.parse_args()
+    B = args.batch
     dev = "cuda:0"
     cfg = O.NFD_CFG
     model, diff = build_model(cfg, O.synth_state_dict(cfg), args.mode, dev)
@@ -42,9 +44,13 @@ def main():
     src = rng.uniform(-0.5, 0.5, size=(4, 3)).astype(np.float32)
     tgt = (src + rng.uniform(-0.2, 0.2, size=(4, 3))).astype(np.float32)
     geo = DragGeometry(src, tgt, 12, 2.0 / 256, 64, 170)
+    if B > 1:
+        geo = [DragGeometry(src, tgt, 12, 2.0 / 256, 64, 170) for _ in range(B)]
     g = torch.Generator().manual_seed(1)
-    x = torch.randn(1, 96, 128, 128, generator=g).to(dev)
+    x = torch.randn(B, 96, 128, 128, generator=g).to(dev)
     origin = torch.randn(3, 64, 64, 170, generator=g).to(dev)
+    if B > 1:
+        origin = torch.stack([origin] * B)
     ops = model._get_ops()
     orig = {f: getattr(ops, f) for f in FAMILIES}
 
