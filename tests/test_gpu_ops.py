@@ -319,3 +319,33 @@ def test_triplane_decode(ops, ref):
     g_out = ops.decode_grid(planes.to(DEV), wd, lin.to(DEV), 3, 11, ops.empty((8 * res * res,)))
     assert float((g_out.cpu() - g_ref).abs().max()) < 2e-4 * max(1.0, float(g_ref.abs().max()))
     assert float(((g_out.cpu() > 0) != (g_ref > 0)).float().mean()) < 1e-3
+
+
+def test_abi_rejects_unsupported_arguments(ops):
+    """The C ABI reports unsupported shapes / inconsistent descriptors as error codes with a message (surfaced as
+    IsbError by the binding) — never a silent fallback, never a launch with garbage parameters."""
+    from ishapediting_b200._lib import IsbError
+
+    dev = ops.device
+    bf = torch.bfloat16
+    a = torch.zeros(1, 16, 16, 48, device=dev, dtype=bf)                 # Cin not a multiple of 64
+    with pytest.raises(IsbError, match="Cin"):
+        ops.conv(a, torch.zeros(64, 9 * 48, device=dev, dtype=bf), None, 3, torch.zeros(1, 16, 16, 64, device=dev))
+    a = torch.zeros(1, 16, 16, 64, device=dev, dtype=bf)
+    with pytest.raises(IsbError, match="ksize"):
+        ops.conv(a, torch.zeros(64, 25 * 64, device=dev, dtype=bf), None, 5, torch.zeros(1, 16, 16, 64, device=dev))
+    with pytest.raises(IsbError, match="gn_slots"):                       # partials buffer sized for another launch
+        ops.conv(torch.zeros(1, 16, 16, 256, device=dev, dtype=bf), torch.zeros(256, 9 * 256, device=dev, dtype=bf), None, 3,
+                 torch.zeros(1, 16, 16, 256, device=dev), gn_part=torch.zeros(1, 32, 999, 2, device=dev))
+    x = torch.zeros(1, 8, 8, 72, device=dev)                             # 72 channels: groups of 2.25
+    with pytest.raises(IsbError, match="groups"):
+        ops.gn_forward(x, None, torch.ones(72, device=dev), torch.zeros(72, device=dev), None, 0, True, 0,
+                       torch.zeros(1, 32, 2, device=dev), torch.zeros(1, 8, 8, 72, device=dev, dtype=bf))
+    qkv = torch.zeros(1, 8, 8, 3 * 2 * 32, device=dev, dtype=bf)        # 32-channel heads: fused path is built for 64
+    with pytest.raises(IsbError, match="channels per head"):
+        ops.attention_flash_forward(qkv, 2, torch.zeros(1, 8, 8, 64, device=dev, dtype=bf), torch.zeros(1, 2, 64, device=dev))
+    # and the library is still healthy afterwards
+    y = torch.empty(1, 16, 16, 64, device=dev)
+    ops.conv(a, torch.zeros(64, 9 * 64, device=dev, dtype=bf), None, 3, y)
+    torch.cuda.synchronize()
+    assert float(y.abs().max()) == 0.0
