@@ -122,53 +122,63 @@ drag_gather_kernel(const DragArgs a) {
   const int x = pix % S, y = pix / S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = DG_THREADS / 32;
 
-  // pass 1: count per warp (each warp owns a contiguous segment of the point list)
-  const int seg = (a.npts + nwarps - 1) / nwarps;
-  const int jbeg = warp * seg, jend = min(a.npts, jbeg + seg);
-  int my_count = 0;
-  for (int j0 = jbeg; j0 < jend; j0 += 32) {
-    const int j = j0 + lane;
-    bool hit = false;
-    if (j < jend) {
-      const int4 bb = __ldg(reinterpret_cast<const int4*>(a.bbox) + pl * a.ngroups + j / a.group_size);
-      if (!(x < bb.x || x > bb.y + 1 || y < bb.z || y > bb.w + 1)) {
-        const float4 info = reinterpret_cast<const float4*>(a.pt_info)[static_cast<size_t>(pl) * a.npts + j];
-        const int ddx = x - static_cast<int>(info.x), ddy = y - static_cast<int>(info.y);
-        hit = ddx >= 0 && ddx <= 1 && ddy >= 0 && ddy <= 1;
-      }
-    }
-    my_count += __popc(__ballot_sync(0xffffffffu, hit));
+  // Four handles cover a few percent of the 3 x S x S pixels: a pixel outside every handle's bounding box has no
+  // contributing sample point and skips both list passes (CTA-uniform test, so the barriers inside stay legal).
+  bool any = false;
+  for (int gi = 0; gi < a.ngroups; ++gi) {
+    const int4 bb = __ldg(reinterpret_cast<const int4*>(a.bbox) + pl * a.ngroups + gi);
+    any |= !(x < bb.x || x > bb.y + 1 || y < bb.z || y > bb.w + 1);
   }
-  if (lane == 0) s_cnt[warp] = my_count;
-  __syncthreads();
   int base = 0, total = 0;
-  for (int w = 0; w < nwarps; ++w) {
-    if (w < warp) base += s_cnt[w];
-    total += s_cnt[w];
-  }
-  // pass 2: ordered compaction into the shared list
-  if (total > 0 && total <= DG_MAXLIST) {
-    int pos = base;
+  if (any) {
+    // pass 1: count per warp (each warp owns a contiguous segment of the point list)
+    const int seg = (a.npts + nwarps - 1) / nwarps;
+    const int jbeg = warp * seg, jend = min(a.npts, jbeg + seg);
+    int my_count = 0;
     for (int j0 = jbeg; j0 < jend; j0 += 32) {
       const int j = j0 + lane;
       bool hit = false;
-      float w = 0.f;
       if (j < jend) {
         const int4 bb = __ldg(reinterpret_cast<const int4*>(a.bbox) + pl * a.ngroups + j / a.group_size);
         if (!(x < bb.x || x > bb.y + 1 || y < bb.z || y > bb.w + 1)) {
           const float4 info = reinterpret_cast<const float4*>(a.pt_info)[static_cast<size_t>(pl) * a.npts + j];
           const int ddx = x - static_cast<int>(info.x), ddy = y - static_cast<int>(info.y);
           hit = ddx >= 0 && ddx <= 1 && ddy >= 0 && ddy <= 1;
-          if (hit) w = (ddx ? info.z : 1.0f - info.z) * (ddy ? info.w : 1.0f - info.w);
         }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const int k = pos + __popc(m & ((1u << lane) - 1u));
-        s_j[k] = j;
-        s_w[k] = w;
+      my_count += __popc(__ballot_sync(0xffffffffu, hit));
+    }
+    if (lane == 0) s_cnt[warp] = my_count;
+    __syncthreads();
+    base = 0;
+    for (int w = 0; w < nwarps; ++w) {
+      if (w < warp) base += s_cnt[w];
+      total += s_cnt[w];
+    }
+    // pass 2: ordered compaction into the shared list
+    if (total > 0 && total <= DG_MAXLIST) {
+      int pos = base;
+      for (int j0 = jbeg; j0 < jend; j0 += 32) {
+        const int j = j0 + lane;
+        bool hit = false;
+        float w = 0.f;
+        if (j < jend) {
+          const int4 bb = __ldg(reinterpret_cast<const int4*>(a.bbox) + pl * a.ngroups + j / a.group_size);
+          if (!(x < bb.x || x > bb.y + 1 || y < bb.z || y > bb.w + 1)) {
+            const float4 info = reinterpret_cast<const float4*>(a.pt_info)[static_cast<size_t>(pl) * a.npts + j];
+            const int ddx = x - static_cast<int>(info.x), ddy = y - static_cast<int>(info.y);
+            hit = ddx >= 0 && ddx <= 1 && ddy >= 0 && ddy <= 1;
+            if (hit) w = (ddx ? info.z : 1.0f - info.z) * (ddy ? info.w : 1.0f - info.w);
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const int k = pos + __popc(m & ((1u << lane) - 1u));
+          s_j[k] = j;
+          s_w[k] = w;
+        }
+        pos += __popc(m);
       }
-      pos += __popc(m);
     }
   }
   __syncthreads();
@@ -214,14 +224,18 @@ drag_gather_kernel(const DragArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 drag_loss_kernel(const DragArgs a) {
   pdl_wait();      // predecessor complete and flushed
   pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
-  __shared__ double red[2][8];
+  // one CTA (the sum must have a fixed order) but 1024 threads with four loads in flight each: this kernel sits
+  // between the gather and the backward pass on the critical path
+  __shared__ double red[2][32];
   double motion = 0, mask = 0;
   const int n_motion = 3 * a.npts;
+#pragma unroll 4
   for (int i = threadIdx.x; i < n_motion; i += blockDim.x) motion += a.partial[i];
+#pragma unroll 4
   for (int i = threadIdx.x; i < a.n_gather_blocks; i += blockDim.x) mask += a.partial[n_motion + i];
   motion = warp_sum_d(motion);
   mask = warp_sum_d(mask);
@@ -229,7 +243,7 @@ drag_loss_kernel(const DragArgs a) {
   __syncthreads();
   if (threadIdx.x == 0) {
     double mo = 0, ma = 0;
-    for (int w = 0; w < 8; ++w) { mo += red[0][w]; ma += red[1][w]; }
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) { mo += red[0][w]; ma += red[1][w]; }
     const double inv_count = a.dyn ? a.dyn[0] : a.inv_count;
     const double mnorm = a.dyn ? a.dyn[1] : (a.mask_count > 0 ? 1.0 / (static_cast<double>(a.Ca) * a.mask_count) : 0.0);
     double loss = -mo * inv_count;
@@ -280,7 +294,7 @@ int isb_drag_loss_grad(const isb_drag_desc* d, isb_stream_t stream) {
   ISB_LAUNCH_CHECK();
   ISB_CUDA(isb::launch(isb::drag_gather_kernel, dim3(d->S * d->S, 3), isb::DG_THREADS, 0, st, a));
   ISB_LAUNCH_CHECK();
-  ISB_CUDA(isb::launch(isb::drag_loss_kernel, 1, 256, 0, st, a));
+  ISB_CUDA(isb::launch(isb::drag_loss_kernel, 1, 1024, 0, st, a));
   ISB_LAUNCH_CHECK();
   return ISB_OK;
 }
