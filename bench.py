@@ -341,7 +341,11 @@ def run_ours(args):
                        "l2_policy": "working set > L2: 1.57 GB of bf16 weight panels streamed per step vs 126 MB L2",
                        "weights": "synthetic seeded (oracle.synth_state_dict)", "setup_s": round(setup_s, 2)},
             "e2e": {"value": world * n_e2e / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / n_e2e},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / n_e2e,
+                    "how": "HostStepPipeline: pinned host buffers; every step's inputs are copied H2D and its latent + "
+                           "loss D2H inside the timed region and read by the host; the copies of step k+1 / k-1 run on "
+                           "copy streams while step k computes (synchronous copies cost +0.39 ms/step)",
+                    "loss_checksum": checksum},
             "edit": {"edits_per_s": world / (ms_edit / 1e3), "ms_per_edit": ms_edit,
                      "what": f"{W_TIME} guided steps + {DECODE_RES}^3 occupancy decode via DragStuff.training"},
             "step_tflops": STEP_GFLOP / (ms / args.steps),
