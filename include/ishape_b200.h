@@ -306,6 +306,14 @@ int isb_triplane_decode_points(const float* planes_hwc, int R, const isb_triplan
                                const float* coords, int64_t npts, float* out,
                                isb_stream_t stream);
 
+/* Gradient of sum_i d_logits[i] * logit_i w.r.t. the three planes, ADDED to d_planes_hwc [3,R,R,32] (the caller
+ * zero-fills it): the autograd backward of MultiTriplane.forward that the reference's reconstruction guidance
+ * runs (drag_utils.py:443-463, loss.backward() through axisnetworks.py:546-562 into pred_xstart).  The forward is
+ * recomputed in fp32; the bilinear scatter uses float atomics (summation order not fixed). */
+int isb_triplane_decode_points_backward(const float* planes_hwc, int R, const isb_triplane_mlp* w,
+                                        const float* coords, int64_t npts, const float* d_logits,
+                                        float* d_planes_hwc, isb_stream_t stream);
+
 /* ---- introspection ---------------------------------------------------- */
 /* Number of kernels this library has launched in this process (all threads). */
 uint64_t isb_launch_count(void);

@@ -134,6 +134,8 @@ PROTOTYPES = {
                                          c_void_p, c_void_p]),
     "isb_triplane_decode_points": (c_int, [c_void_p, c_int, C.POINTER(TriplaneMlp), c_void_p, C.c_int64,
                                            c_void_p, c_void_p]),
+    "isb_triplane_decode_points_backward": (c_int, [c_void_p, c_int, C.POINTER(TriplaneMlp), c_void_p, C.c_int64,
+                                                    c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -210,6 +210,197 @@ triplane_decode_kernel(const DecodeArgs a) {
   }
 }
 
+// ---- backward w.r.t. the planes -----------------------------------------------------
+// The reference's real-shape reconstruction guidance (drag_utils.py:443-463) back-propagates a BCE loss on ~40 000
+// sample points through MultiTriplane.forward into the three feature planes (= pred_xstart of the diffusion step).
+// One CTA per 32-point tile recomputes the forward in fp32 FFMA (exact, the point count is small), walks the MLP
+// backwards with the weights in shared memory and scatters w_corner * dL/df into the four corners of each plane with
+// float atomics (the only non-deterministic summation order in the library; documented in the header).
+constexpr int DB_TP = 32;
+constexpr int DB_THREADS = 256;
+struct DecodeBwdSmem {
+  float W1[DC_H][DC_LD];
+  float W2[DC_H][DC_LD];
+  float Bm[DC_F][DC_M];
+  float b1[DC_H], b2[DC_H], w3[DC_H];
+  float A0[DB_TP][DC_LD];    // [sin | cos]            later: d(theta)
+  float A1[DB_TP][DC_LD];    // relu(h1)               later: dL/dh1 (masked)
+  float A2[DB_TP][DC_LD];    // relu(h2)               later: dL/dh2 (masked), then dL/dA0
+  float F[DB_TP][DC_F + 1];  // sampled features       later: dL/df
+};
+struct DecodeBwdArgs {
+  const float* planes; int R;
+  const float* fourier_B; const float* w1; const float* b1; const float* w2; const float* b2; const float* w3;
+  const float* coords; long long npts;
+  const float* d_logits;
+  float* d_planes;
+};
+
+// bilinear corner weights of one plane sample (align_corners=True, zeros padding), as in sample_plane8
+struct Corner4 {
+  int x0, y0;
+  float fx, fy;
+};
+__device__ __forceinline__ Corner4 plane_corners(int R, float gx, float gy) {
+  const float ix = ((gx + 1.0f) / 2.0f) * static_cast<float>(R - 1);
+  const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(R - 1);
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  return Corner4{static_cast<int>(fx0), static_cast<int>(fy0), ix - fx0, iy - fy0};
+}
+
+// out[pt][o] = sum_k in[pt][k] * W[o][k]   (FWD)   or   out[pt][k] = sum_o in[pt][o] * W[o][k]   (!FWD)
+// thread (pt = tid/8, lane8 = tid%8) owns the 16 outputs lane8 + 8 j: conflict-free with the 132-float row pitch
+template <bool FWD>
+__device__ __forceinline__ void db_matvec(const float (*W)[DC_LD], const float (*in)[DC_LD], float* acc, int pt, int l8) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < DC_H; ++r) {
+    const float a = in[pt][r];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = fmaf(a, FWD ? W[l8 + 8 * j][r] : W[r][l8 + 8 * j], acc[j]);
+  }
+}
+
+__global__ void __launch_bounds__(DB_THREADS, 1)
+triplane_decode_bwd_kernel(const DecodeBwdArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(16) uint8_t dsm_raw[];
+  DecodeBwdSmem& s = *reinterpret_cast<DecodeBwdSmem*>(dsm_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < DC_H * DC_H; i += DB_THREADS) {
+    s.W1[i / DC_H][i % DC_H] = __ldg(a.w1 + i);
+    s.W2[i / DC_H][i % DC_H] = __ldg(a.w2 + i);
+  }
+  for (int i = tid; i < DC_F * DC_M; i += DB_THREADS) s.Bm[i / DC_M][i % DC_M] = __ldg(a.fourier_B + i);
+  if (tid < DC_H) { s.b1[tid] = __ldg(a.b1 + tid); s.b2[tid] = __ldg(a.b2 + tid); s.w3[tid] = __ldg(a.w3 + tid); }
+  __syncthreads();
+  const size_t plane_sz = static_cast<size_t>(a.R) * a.R * DC_F;
+  const long long ntiles = (a.npts + DB_TP - 1) / DB_TP;
+  const int pt = tid >> 3, l8 = tid & 7;
+  const float two_pi = 6.283185307179586f;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long ip = tile * DB_TP + pt;
+    const bool live = ip < a.npts;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (live) { cx = __ldg(a.coords + ip * 3); cy = __ldg(a.coords + ip * 3 + 1); cz = __ldg(a.coords + ip * 3 + 2); }
+    const float gxs[3] = {cx, cy, cx}, gys[3] = {cy, cz, cz};   // xy, yz, xz planes (x->W, y->H of each)
+    const int c0 = l8 * 4;
+    // 1. features: 4 channels per thread
+    {
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      if (live) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          const Corner4 q = plane_corners(a.R, gxs[pl], gys[pl]);
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              const int x = q.x0 + dx, y = q.y0 + dy;
+              if (x < 0 || x >= a.R || y < 0 || y >= a.R) continue;
+              const float w = (dx ? q.fx : 1.0f - q.fx) * (dy ? q.fy : 1.0f - q.fy);
+              const float4 v = __ldg(reinterpret_cast<const float4*>(a.planes + pl * plane_sz + (static_cast<size_t>(y) * a.R + x) * DC_F + c0));
+              f[0] = fmaf(w, v.x, f[0]); f[1] = fmaf(w, v.y, f[1]); f[2] = fmaf(w, v.z, f[2]); f[3] = fmaf(w, v.w, f[3]);
+            }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s.F[pt][c0 + j] = f[j];
+    }
+    __syncthreads();
+    // 2. Fourier features: thread owns frequencies l8 + 8 j
+    {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int m = l8 + 8 * j;
+        float u = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < DC_F; ++c) u = fmaf(s.F[pt][c], s.Bm[c][m], u);
+        float sv, cv;
+        sincosf(two_pi * u, &sv, &cv);
+        s.A0[pt][m] = sv;
+        s.A0[pt][DC_M + m] = cv;
+      }
+    }
+    __syncthreads();
+    float acc[16];
+    db_matvec<true>(s.W1, s.A0, acc, pt, l8);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s.A1[pt][l8 + 8 * j] = fmaxf(acc[j] + s.b1[l8 + 8 * j], 0.f);
+    __syncthreads();
+    db_matvec<true>(s.W2, s.A1, acc, pt, l8);
+    const float dl = live ? __ldg(a.d_logits + ip) : 0.f;
+    // 3. dL/dh2 (masked by the ReLU of layer 2) straight from the output layer
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int o = l8 + 8 * j;
+      s.A2[pt][o] = (acc[j] + s.b2[o] > 0.f) ? dl * s.w3[o] : 0.f;
+    }
+    __syncthreads();
+    // 4. dL/dh1 = (dL/dh2 @ W2) masked by the ReLU of layer 1
+    db_matvec<false>(s.W2, s.A2, acc, pt, l8);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int k = l8 + 8 * j;
+      s.A1[pt][k] = s.A1[pt][k] > 0.f ? acc[j] : 0.f;
+    }
+    __syncthreads();
+    // 5. dL/dA0 = dL/dh1 @ W1
+    db_matvec<false>(s.W1, s.A1, acc, pt, l8);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s.A2[pt][l8 + 8 * j] = acc[j];
+    __syncthreads();
+    // 6. d(theta) = dsin * cos - dcos * sin;  dL/du = 2 pi d(theta)   (kept in A0[pt][0..63])
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int m = l8 + 8 * j;
+      const float sv = s.A0[pt][m], cv = s.A0[pt][DC_M + m];
+      const float dth = s.A2[pt][m] * cv - s.A2[pt][DC_M + m] * sv;
+      s.A1[pt][m] = two_pi * dth;          // A1 is free again (its owner finished step 5 before the barrier)
+    }
+    __syncthreads();
+    // 7. dL/df = dL/du @ B^T, 4 channels per thread, then the bilinear scatter
+    {
+      float df[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+      for (int m = 0; m < DC_M; ++m) {
+        const float du = s.A1[pt][m];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) df[j] = fmaf(du, s.Bm[c0 + j][m], df[j]);
+      }
+      if (live) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          const Corner4 q = plane_corners(a.R, gxs[pl], gys[pl]);
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              const int x = q.x0 + dx, y = q.y0 + dy;
+              if (x < 0 || x >= a.R || y < 0 || y >= a.R) continue;
+              const float w = (dx ? q.fx : 1.0f - q.fx) * (dy ? q.fy : 1.0f - q.fy);
+              float* dst = a.d_planes + pl * plane_sz + (static_cast<size_t>(y) * a.R + x) * DC_F + c0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) atomicAdd(dst + j, w * df[j]);
+            }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int decode_bwd_launch(const DecodeBwdArgs& a, cudaStream_t st) {
+  const long long ntiles = (a.npts + DB_TP - 1) / DB_TP;
+  const long long blocks = ntiles < num_sms() ? ntiles : num_sms();
+  if (blocks < 1) return ISB_OK;
+  ISB_CUDA(isb::launch(triplane_decode_bwd_kernel, static_cast<int>(blocks), DB_THREADS, sizeof(DecodeBwdSmem), st, a));
+  ISB_LAUNCH_CHECK();
+  return ISB_OK;
+}
+
 static int decode_launch(const DecodeArgs& a, bool grid_mode, cudaStream_t st) {
   const long long ntiles = (a.npts + DC_TP - 1) / DC_TP;
   long long blocks = ntiles < num_sms() ? ntiles : num_sms();
@@ -224,6 +415,7 @@ static int decode_launch(const DecodeArgs& a, bool grid_mode, cudaStream_t st) {
 int decode_init() {
   ISB_CUDA(cudaFuncSetAttribute(triplane_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(DecodeSmem)));
   ISB_CUDA(cudaFuncSetAttribute(triplane_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(DecodeSmem)));
+  ISB_CUDA(cudaFuncSetAttribute(triplane_decode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(DecodeBwdSmem)));
   return ISB_OK;
 }
 
@@ -247,6 +439,15 @@ int isb_triplane_decode_points(const float* planes_hwc, int R, const isb_triplan
   isb::DecodeArgs a{planes_hwc, R, w->fourier_B, w->w1, w->b1, w->w2, w->b2, w->w3, w->b3,
                     nullptr, 0, 0, coords, static_cast<long long>(npts), out};
   return isb::decode_launch(a, false, isb::as_stream(stream));
+}
+
+int isb_triplane_decode_points_backward(const float* planes_hwc, int R, const isb_triplane_mlp* w, const float* coords,
+                                        int64_t npts, const float* d_logits, float* d_planes_hwc, isb_stream_t stream) {
+  ISB_CHECK_ARG(planes_hwc && w && coords && d_logits && d_planes_hwc && npts >= 0 && R > 1,
+                "isb_triplane_decode_points_backward: bad arguments");
+  isb::DecodeBwdArgs a{planes_hwc, R, w->fourier_B, w->w1, w->b1, w->w2, w->b2, w->w3,
+                       coords, static_cast<long long>(npts), d_logits, d_planes_hwc};
+  return isb::decode_bwd_launch(a, isb::as_stream(stream));
 }
 
 }  // extern "C"

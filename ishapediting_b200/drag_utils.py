@@ -5,7 +5,7 @@ update_latent_params (:252-280), get_mesh (:282-300), training (:302-399, a gene
 progress), latent_inversion (:552-566), clear_params / reset_params / set_offset1 and the attributes
 the GUI reads (w, w0, feature_guidance, variance, variance_noise, train_flag, r1, offset1,
 voxel_size).  Out of scope here: checkpoint discovery on disk (update_model_params :210-250 — weights
-are loaded with load_state_dict), train_triplane (:401-471), Open3D meshing.
+are loaded with load_state_dict), Open3D meshing and the mesh -> occupancy sampling inside train_triplane (:411-440).
 
 What differs from the reference, by design:
   * the guided step never enters torch.autograd: UNet forward plan -> isb_drag_loss_grad -> UNet
@@ -390,6 +390,32 @@ class HostStepPipeline:
         return self.img_host[s], self.loss_host[s]
 
 
+def recon_guided_step(model, diffusion, decoder, img, i, coords, gt, scale=600.0, noise=None, rng=1.0, middle=0.0):
+    """One iteration of the reference's real-shape reconstruction guidance (drag_utils.py:445-463, SURVEY.md §8f
+    rank 2): classifier guidance on the predicted x_start through the triplane decoder.  img (1,96,R,R) latent at
+    respaced step i; coords (P,3) in [-1,1]; gt (P,1) occupancies in {0,1}.  Returns (next latent, loss).
+    The UNet forward and its FULL input-gradient backward (out layer and output blocks 9-14 included) run on the
+    kernel plan behind the autograd bridge; the decoder forward / backward are isb_triplane_decode_points(_backward);
+    the posterior algebra in between is elementwise torch (gaussian_diffusion.p_mean_variance, grad route)."""
+    dev = img.device
+    img = img.detach().clone().requires_grad_(True)
+    outs = diffusion.p_sample_guidance(model, img, th.tensor([i], device=dev), noise=noise)
+    R = img.shape[-1]
+    predict_x0 = (outs["pred_xstart"] * rng + middle).reshape(3, 32, R, R)
+    for j in range(3):
+        decoder.embeddings[j] = predict_x0[[j]]
+    prediction = decoder(0, coords.to(dev).unsqueeze(0)).squeeze(0)
+    gt = gt.to(dev)
+    assert gt.shape == prediction.shape
+    loss = -th.nn.BCEWithLogitsLoss()(prediction, gt)
+    loss.backward()
+    with th.no_grad():
+        nxt = (outs["sample"] + outs["variance"] * (scale * img.grad)).clone().detach()
+    for j in range(3):          # do not keep the autograd graph alive through the decoder's plane list
+        decoder.embeddings[j] = decoder.embeddings[j].detach()
+    return nxt, loss.detach()
+
+
 # ------------------------------------------------------------------------------------------------------
 # DragStuff
 # ------------------------------------------------------------------------------------------------------
@@ -529,6 +555,34 @@ class DragStuff:
             if hasattr(mesh, "filter_smooth_simple"):
                 return mesh.filter_smooth_simple(number_of_iterations=10)
             return mesh
+
+    # ---- real-shape reconstruction guidance (reference :400-471) ---------------------------
+    def recon_guided_step(self, img, i, coords, gt, scale=600.0, noise=None):
+        """Loop body of train_triplane (:445-463), see the module-level recon_guided_step."""
+        return recon_guided_step(self.model, self.diffusion, self.decoder, img, i, coords, gt, scale=scale, noise=noise,
+                                 rng=self.range, middle=self.middle)
+
+    def train_triplane(self, points=None, occupancies=None, tri_feat=None, scale=600, batch_size=40000, seed=None):
+        """Reference :400-471.  The mesh -> (points, occupancies) sampling of :411-440 is Open3D / CPU code outside
+        the path: pass the samples directly (`points` (M,3) float32 in [-1,1], `occupancies` (M,) or (M,1) in {0,1}),
+        or a ready `tri_feat` latent as the reference's `tri_feat_path` branch does.  Returns the reconstructed
+        latent; sets self.mesh / self.mesh0 like the reference."""
+        if tri_feat is not None:
+            img = th.as_tensor(tri_feat, device=self.device, dtype=th.float32)
+        else:
+            pts = th.as_tensor(np.asarray(points), dtype=th.float32)
+            occ = th.as_tensor(np.asarray(occupancies), dtype=th.float32).reshape(-1, 1)
+            g = th.Generator().manual_seed(seed) if seed is not None else None
+            R = self.args.image_size
+            img = th.randn((1, 96, R, R), generator=g).to(self.device)
+            for i in range(self.args.num_steps - 1, -1, -1):
+                idx = th.randperm(pts.shape[0], generator=g)[:batch_size]     # DataLoader(shuffle=True) batch, :442,454
+                noise = th.randn((1, 96, R, R), generator=g).to(self.device)
+                img, _ = self.recon_guided_step(img, i, pts[idx], occ[idx], scale=scale, noise=noise)
+        self.clear_params()
+        self.mesh = self.get_mesh(tri_feat=img)
+        self.mesh0 = copy.deepcopy(self.mesh) if not th.is_tensor(self.mesh) else self.mesh.clone()
+        return img
 
     # ---- the guided edit (reference :302-399) -----------------------------------------------------------
     def training(self, sources=None, targets=None, scale=600, cof=0.2, noises=None):

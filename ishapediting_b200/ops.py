@@ -399,6 +399,18 @@ class CudaOps:
                    "isb_triplane_decode_grid")
         return out
 
+    def decode_points_backward(self, planes_hwc, weights, coords, d_logits, d_planes_hwc):
+        """d_planes_hwc (3,R,R,32) += d(sum_i d_logits[i] * logit_i) / d planes   (zero-fill it first)."""
+        for t in (planes_hwc, coords, d_logits, d_planes_hwc):
+            _chk(t, torch.float32)
+        assert d_planes_hwc.shape == planes_hwc.shape and d_logits.numel() == coords.shape[0]
+        m = self._mlp(weights)
+        _lib.check(self.lib.isb_triplane_decode_points_backward(_p(planes_hwc), planes_hwc.shape[1], C.byref(m),
+                                                                _p(coords), coords.shape[0], _p(d_logits),
+                                                                _p(d_planes_hwc), _stream()),
+                   "isb_triplane_decode_points_backward")
+        return d_planes_hwc
+
     def decode_points(self, planes_hwc, weights, coords, out):
         _chk(planes_hwc, torch.float32); _chk(coords, torch.float32); _chk(out, torch.float32)
         m = self._mlp(weights)

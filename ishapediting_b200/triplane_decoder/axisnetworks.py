@@ -16,6 +16,28 @@ class FourierFeatureTransform(nn.Module):
         self._B = nn.Parameter(torch.randn((num_input_channels, mapping_size)) * scale, requires_grad=False)
 
 
+class _DecodePoints(torch.autograd.Function):
+    """MultiTriplane.forward with a gradient for the planes (the decoder MLP is frozen, drag_utils.py:248-249):
+    the reference's reconstruction guidance differentiates a BCE loss on sample points w.r.t. pred_xstart
+    (drag_utils.py:443-463)."""
+
+    @staticmethod
+    def forward(ctx, planes_nchw, coords, ops, weights):
+        R = planes_nchw.shape[-1]
+        hwc = ops.to_nhwc(planes_nchw.detach().to(torch.float32).contiguous(), ops.empty((3, R, R, 32)))
+        ctx.ops, ctx.weights, ctx.R = ops, weights, R
+        ctx.save_for_backward(hwc, coords)
+        return ops.decode_points(hwc, weights, coords, ops.empty((coords.shape[0],)))
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        hwc, coords = ctx.saved_tensors
+        ops = ctx.ops
+        d_hwc = ops.zeros((3, ctx.R, ctx.R, 32))
+        ops.decode_points_backward(hwc, ctx.weights, coords, d_logits.detach().to(torch.float32).contiguous(), d_hwc)
+        return ops.to_nchw(d_hwc, ops.empty((3, 32, ctx.R, ctx.R))), None, None, None
+
+
 class MultiTriplane(nn.Module):
     def __init__(self, num_objs, input_dim=3, output_dim=1, noise_val=None, device="cuda"):
         super().__init__()
@@ -75,6 +97,11 @@ class MultiTriplane(nn.Module):
         assert batch == 1
         ops = self._get_ops()
         coords = coordinates.detach().reshape(n, 3).to(device=ops.device, dtype=torch.float32).contiguous()
+        embs = [self.embeddings[3 * obj_idx + i] for i in range(3)]
+        if torch.is_grad_enabled() and any(e.requires_grad for e in embs):
+            # planes that carry a graph (pred_xstart of a guided step): differentiable route
+            planes = torch.cat([e.to(device=ops.device) for e in embs], dim=0)
+            return _DecodePoints.apply(planes, coords, ops, self.mlp_weights()).reshape(1, n, 1)
         out = ops.decode_points(self.planes_hwc(obj_idx), self.mlp_weights(), coords, ops.empty((n,)))
         return out.reshape(1, n, 1)
 

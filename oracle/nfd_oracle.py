@@ -286,7 +286,10 @@ def p_sample_guidance(sd, cfg, sched, x, i, noise, feat_layer=8, clip_denoised=T
     """p_mean_variance + p_sample_guidance for EPSILON / LEARNED_RANGE
     (gaussian_diffusion.py:232-331, 446-510).  `i` is the respaced step index."""
     t_orig = torch.full((x.shape[0],), sched.timestep_map[i], dtype=torch.int64, device=x.device)   # respace.py:122-124
-    model_output, inter = unet_forward(sd, cfg, x, t_orig, feat_layer)
+    if feat_layer >= 0:
+        model_output, inter = unet_forward(sd, cfg, x, t_orig, feat_layer)
+    else:                                                   # unet.py:668-671: no intermediate feature requested
+        model_output, inter = unet_forward(sd, cfg, x, t_orig, feat_layer), None
     C = x.shape[1]
     eps, v = torch.split(model_output, C, dim=1)
     min_log = _f(sched.posterior_log_variance_clipped, i)
@@ -416,6 +419,22 @@ def triplane_forward(w, planes, coords):
     x = F.relu(F.linear(x, w["w1"], w["b1"]))
     x = F.relu(F.linear(x, w["w2"], w["b2"]))
     return F.linear(x, w["w3"], w["b3"]).reshape(-1)
+
+
+def recon_guided_step(sd, cfg, sched, img, i, noise, w_dec, coords, gt, scale=600.0, rng=1.0, middle=0.0):
+    """One iteration of the reference's real-shape reconstruction guidance, drag_utils.py:445-463 (train_triplane):
+    classifier guidance on the predicted x_start — BCE of the decoder's occupancy logits at sampled points against
+    the mesh occupancies, differentiated w.r.t. the noisy latent.  coords (P,3), gt (P,1) in {0,1}."""
+    img = img.detach().clone().requires_grad_(True)
+    outs = p_sample_guidance(sd, cfg, sched, img, i, noise, feat_layer=-1)
+    R = img.shape[-1]
+    planes = (outs["pred_xstart"] * rng + middle).reshape(3, 32, R, R)        # :449-453
+    prediction = triplane_forward(w_dec, planes, coords).reshape(-1, 1)       # :456
+    loss = -F.binary_cross_entropy_with_logits(prediction, gt)               # :458
+    (grad,) = torch.autograd.grad(loss, img)
+    nxt = (outs["sample"] + outs["variance"] * (scale * grad)).detach()       # :460-463
+    return dict(img=nxt, grad=grad.detach(), loss=loss.detach(), pred_xstart=outs["pred_xstart"].detach(),
+                logits=prediction.detach().reshape(-1))
 
 
 def dense_grid_coords(res, x_begin=0, x_end=None):

@@ -11,6 +11,8 @@ deterministic for a given torch version; the fixtures record torch.__version__).
   nfd_step.npz         the same for the real NFD architecture at 96x128x128 — strided sub-samples
                        (every 61st element) + L2 norms, one guided step
   decoder.npz          reference MultiTriplane.forward logits at 4096 seeded points + a 24^3 grid
+  recon_step.npz       one iteration of the reference's reconstruction guidance (train_triplane loop body,
+                       drag_utils.py:445-463) on the small config with 96 latent channels
 """
 import os
 import sys
@@ -121,6 +123,55 @@ def make_decoder():
     print("decoder occupancy", float((grid > 0).float().mean()), float((logits > 0).float().mean()))
 
 
+def recon_cfg():
+    """small_cfg with the 96 latent channels the triplane decoder needs (3 planes x 32 features)."""
+    c = O.small_cfg()
+    c.update(in_out_channels=96)
+    return c
+
+
+def make_recon():
+    """One iteration of the reference's reconstruction guidance (drag_utils.py:445-463) with the reference's own
+    diffusion, UNet and MultiTriplane modules: classifier guidance on pred_xstart through the decoder."""
+    cfg = recon_cfg()
+    ns, model, diffusion = R.reference_model_and_diffusion(cfg)
+    sd = O.synth_state_dict(cfg)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    Rz = cfg["image_size"]
+    w, _ = O.synth_decoder(R=Rz)
+    dec = ns.axisnetworks.MultiTriplane(1, input_dim=3, output_dim=1, device="cpu")
+    dec.net[0]._B.data.copy_(w["B"])
+    for idx, k in ((1, "1"), (3, "2"), (5, "3")):
+        dec.net[idx].weight.data.copy_(w["w" + k])
+        dec.net[idx].bias.data.copy_(w["b" + k])
+    for prm in dec.parameters():
+        prm.requires_grad_(False)                     # drag_utils.py:248-249
+    dec.eval()
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(1, 96, Rz, Rz, generator=g)
+    noise = torch.randn(1, 96, Rz, Rz, generator=g)
+    coords = torch.rand(3000, 3, generator=g) * 2 - 1
+    gt = (torch.rand(3000, 1, generator=g) < 0.3).float()
+    i, scale = 120, 600
+    img = x.clone().requires_grad_(True)
+    outs = diffusion.p_sample_guidance(model, img, torch.tensor([i]), noise=noise)
+    predict_x0 = (outs["pred_xstart"] * 1.0 + 0.0).reshape(3, 32, Rz, Rz)
+    for j in range(3):
+        dec.embeddings[j] = predict_x0[[j]]
+    prediction = dec(0, coords.unsqueeze(0)).squeeze(0)
+    assert gt.shape == prediction.shape
+    loss = -torch.nn.BCEWithLogitsLoss()(prediction, gt)
+    loss.backward()
+    grads = scale * img.grad.clone().detach()
+    with torch.no_grad():
+        nxt = (outs["sample"] + outs["variance"] * grads).clone().detach()
+    np.savez_compressed(os.path.join(HERE, "recon_step.npz"), img=nxt.numpy(), grad=img.grad.numpy(),
+                        loss=np.array(float(loss)), logits=prediction.detach().reshape(-1).numpy(),
+                        meta=np.array([i, scale], dtype=np.float64), torch_version=np.array(torch.__version__))
+    print("recon_step.npz loss", float(loss), "|grad|", float(img.grad.norm()), "|img|", float(nxt.norm()))
+
+
 if __name__ == "__main__":
     assert R.available(), "needs /root/reference"
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -128,5 +179,7 @@ if __name__ == "__main__":
         make_case(O.small_cfg(), "small_unet_step.npz", w_time=2, r1=3, voxel=2.0 / 64, full=True)
     if which in ("all", "decoder"):
         make_decoder()
+    if which in ("all", "recon"):
+        make_recon()
     if which in ("all", "nfd"):
         make_case(O.NFD_CFG, "nfd_step.npz", w_time=2, r1=12, voxel=2.0 / 256, full=False)

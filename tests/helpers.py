@@ -45,3 +45,38 @@ def drag_problem(cfg, sd, sched, x2, noise, i, g, n_handles=4, r1=None, voxel=No
     voxel = 2.0 / 256 if voxel is None else voxel
     pg, sg, masks = O.drag_setup(src, tgt, r1, voxel, S)
     return origin, src, tgt, r1, voxel, pg, sg, masks
+
+
+def recon_cfg():
+    """small_cfg with the 96 latent channels the triplane decoder needs (tests/golden/make_golden.py:recon_cfg)."""
+    c = O.small_cfg()
+    c.update(in_out_channels=96)
+    return c
+
+
+def recon_inputs(R, n_pts=3000, seed=21):
+    """The seeded inputs of tests/golden/recon_step.npz: latent, noise, sample points, occupancies."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(1, 96, R, R, generator=g)
+    noise = torch.randn(1, 96, R, R, generator=g)
+    coords = torch.rand(n_pts, 3, generator=g) * 2 - 1
+    gt = (torch.rand(n_pts, 1, generator=g) < 0.3).float()
+    return x, noise, coords, gt
+
+
+def build_decoder(R, device, ops=None):
+    """The product MultiTriplane carrying oracle.synth_decoder's MLP."""
+    from ishapediting_b200.triplane_decoder.axisnetworks import MultiTriplane
+
+    w, planes = O.synth_decoder(R=R)
+    dec = MultiTriplane(1, device=str(device))
+    dec.net[0]._B.data.copy_(w["B"])
+    for idx, k in ((1, "1"), (3, "2"), (5, "3")):
+        dec.net[idx].weight.data.copy_(w["w" + k])
+        dec.net[idx].bias.data.copy_(w["b" + k])
+    dec.to(device)
+    for prm in dec.parameters():
+        prm.requires_grad_(False)
+    if ops is not None:
+        dec.set_ops(ops)
+    return dec, w, planes

@@ -329,6 +329,13 @@ class RefOps:
         out.copy_(self._decode(planes_hwc, weights, coords))
         return out
 
+    def decode_points_backward(self, planes_hwc, weights, coords, d_logits, d_planes_hwc):
+        p = planes_hwc.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            (g,) = torch.autograd.grad((self._decode(p, weights, coords) * d_logits).sum(), p)
+        d_planes_hwc.add_(g)
+        return d_planes_hwc
+
     def decode_grid(self, planes_hwc, weights, lin, x_begin, x_end, out):
         xs, ys, zs = torch.meshgrid([lin[x_begin:x_end], lin, lin], indexing="ij")
         coords = torch.stack([xs, ys, zs], -1).reshape(-1, 3)

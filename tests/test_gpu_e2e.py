@@ -113,3 +113,27 @@ def test_latent_inversion_flow_fp32():
             o = O.p_sample_guidance(sd, cfg, sched, img, i, torch.zeros_like(img), feat_layer=5)
             img = o["mean"] + ds.variance_noise[k].cpu()
     assert float((img - x0.cpu()).abs().max()) < 5e-4
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-3), ("bf16", 3e-2)])
+def test_recon_guided_step(mode, tol):
+    """One iteration of the reference's reconstruction guidance (train_triplane, drag_utils.py:445-463) on the GPU:
+    UNet forward + FULL input-gradient backward on the kernel plan, decoder forward / backward kernels.  The fp32
+    tolerance reflects the conditioning of the decoder gradient (tests/test_host_logic.py), not kernel error."""
+    from ishapediting_b200.drag_utils import recon_guided_step
+    from tests.helpers import build_decoder, build_model, recon_inputs
+
+    cfg = O.mid_cfg()
+    cfg.update(in_out_channels=96)
+    sd = O.synth_state_dict(cfg)
+    R = cfg["image_size"]
+    model, diff = build_model(cfg, sd, mode, DEV)
+    dec, w, _ = build_decoder(R, DEV)
+    sched = O.Schedule(cfg["diffusion_steps"], cfg["timestep_respacing"])
+    x, noise, coords, gt = recon_inputs(R, n_pts=2000)
+    ref = O.recon_guided_step(sd, cfg, sched, x, 120, noise, w, coords, gt, scale=600.0)
+    nxt, loss = recon_guided_step(model, diff, dec, x.to(DEV), 120, coords, gt, scale=600.0, noise=noise.to(DEV))
+    err = rel_l2(nxt, ref["img"])
+    print("recon", mode, {"img": err, "loss": abs(float(loss) - float(ref["loss"]))})
+    assert err < tol
+    assert abs(float(loss) - float(ref["loss"])) < (1e-4 if mode == "fp32" else 2e-2)

@@ -117,6 +117,40 @@ def test_fused_gn_statistics_plan_mid_bf16(monkeypatch):
     assert fused_fwd > 0 and fused_bwd > 0
 
 
+def test_recon_guided_step_matches_oracle():
+    """train_triplane's loop body through the product surface (autograd bridge of the UNet plan, differentiable
+    posterior route, MultiTriplane with its custom backward) against the oracle, fp32, torch mirror of the kernels."""
+    from ishapediting_b200.drag_utils import recon_guided_step
+    from tests.helpers import build_decoder, recon_cfg, recon_inputs
+
+    cfg = recon_cfg()
+    sd = O.synth_state_dict(cfg)
+    ops = RefOps("fp32")
+    model, diff = build_model(cfg, sd, "fp32", "cpu", ops)
+    dec, w, _ = build_decoder(cfg["image_size"], "cpu", ops)
+    sched = O.Schedule(cfg["diffusion_steps"], cfg["timestep_respacing"])
+    x, noise, coords, gt = recon_inputs(cfg["image_size"], n_pts=500)
+    ref = O.recon_guided_step(sd, cfg, sched, x, 120, noise, w, coords, gt, scale=600.0)
+    nxt, loss = recon_guided_step(model, diff, dec, x, 120, coords, gt, scale=600.0, noise=noise)
+    # The decoder gradient is ill-conditioned in fp32 (sin/cos of ~50 rad arguments, ReLU masks, few points): the
+    # ORACLE's own gradient moves by 0.8 % when its planes are perturbed by 1e-6 relative, and by 0.14 % between fp32
+    # and fp64.  The two sides agree on pred_xstart to 7e-7, hence on the gradient to ~1 % and on the next latent
+    # (of which the guidance term is a small part) to a few 1e-4.  The decoder backward itself is checked on
+    # identical inputs below, where it is exact.
+    assert rel_l2(nxt, ref["img"]) < 1e-3
+    assert abs(float(loss) - float(ref["loss"])) < 1e-5
+    planes = ref["pred_xstart"].reshape(3, 32, 32, 32).clone().requires_grad_(True)
+    import torch.nn.functional as F
+    lo = -F.binary_cross_entropy_with_logits(O.triplane_forward(w, planes, coords).reshape(-1, 1), gt)
+    (g_ref,) = torch.autograd.grad(lo, planes)
+    p2 = ref["pred_xstart"].reshape(3, 32, 32, 32).clone().requires_grad_(True)
+    for j in range(3):
+        dec.embeddings[j] = p2[[j]]
+    lp = -torch.nn.BCEWithLogitsLoss()(dec(0, coords.unsqueeze(0)).squeeze(0), gt)
+    lp.backward()
+    assert rel_l2(p2.grad, g_ref) < 1e-5
+
+
 def test_diffusion_tables_and_respacing(small):
     _, _, _, diff = small
     sched = O.Schedule(1000, "200")

@@ -82,6 +82,25 @@ def test_oracle_decoder_matches_reference_golden():
     assert 0.1 < float((grid > 0).float().mean()) < 0.5      # non-trivial surface
 
 
+def test_oracle_recon_guidance_matches_reference_golden():
+    """One iteration of the reference's reconstruction guidance (train_triplane loop body, drag_utils.py:445-463,
+    run with the reference's own UNet / diffusion / MultiTriplane): next latent, input gradient, loss, logits."""
+    from tests.helpers import recon_cfg, recon_inputs
+
+    z = np.load(os.path.join(GOLD, "recon_step.npz"))
+    cfg = recon_cfg()
+    sd = O.synth_state_dict(cfg)
+    sched = O.Schedule(cfg["diffusion_steps"], cfg["timestep_respacing"])
+    x, noise, coords, gt = recon_inputs(cfg["image_size"])
+    w, _ = O.synth_decoder(R=cfg["image_size"])
+    i, scale = int(z["meta"][0]), float(z["meta"][1])
+    r = O.recon_guided_step(sd, cfg, sched, x, i, noise, w, coords, gt, scale=scale)
+    assert rel_l2(r["img"], torch.from_numpy(z["img"])) < 2e-5
+    assert rel_l2(r["grad"], torch.from_numpy(z["grad"])) < 2e-4
+    assert abs(float(r["loss"]) - float(z["loss"])) < 1e-6
+    assert float((r["logits"] - torch.from_numpy(z["logits"])).abs().max()) < 2e-5
+
+
 def test_schedule_matches_published_constants():
     """200-of-1000 respacing map and table shapes."""
     s = O.Schedule(1000, "200")
