@@ -277,17 +277,51 @@ class GaussianDiffusion:
         return {"sample": mean_pred + nonzero * sigma * noise, "pred_xstart": out["pred_xstart"],
                 "inter_feat": out["inter_feat"], "model_output": out["model_output"]}
 
-    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
-                         model_kwargs=None, device=None, progress=False, eta=0.0):
+    def ddim_guidance_sample(self, eps, grads, xt, t, clip_denoised=True):
+        """Reference :707-716: deterministic DDIM update with a classifier-guidance gradient folded into eps
+        (eps <- eps - sqrt(1 - abar_t) * grads; like the reference, `eps` is updated in place)."""
+        eps -= _extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, eps.shape) * grads
+        x0 = self._predict_xstart_from_eps(xt, t, eps)
+        if clip_denoised:
+            x0 = x0.clamp(-1, 1)
+        eps = self._predict_eps_from_xstart(xt, t, x0)
+        abar_prev = _extract_into_tensor(self.alphas_cumprod_prev, t, eps.shape)
+        return x0 * th.sqrt(abar_prev) + th.sqrt(1 - abar_prev) * eps
+
+    def ddim_reverse_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None, eta=0.0):
+        """Reference :718-761: x_{t+1} from x_t along the deterministic DDIM ODE."""
+        assert eta == 0.0, "Reverse ODE only for deterministic path"
+        out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                   model_kwargs=model_kwargs)
+        eps = self._predict_eps_from_xstart(x, t, out["pred_xstart"])
+        abar_next = _extract_into_tensor(self.alphas_cumprod_next, t, x.shape)
+        return {"sample": out["pred_xstart"] * th.sqrt(abar_next) + th.sqrt(1 - abar_next) * eps,
+                "pred_xstart": out["pred_xstart"]}
+
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                     model_kwargs=None, device=None, progress=False, eta=0.0):
+        """Reference :799-840: generator over the DDIM steps (yields each step's dict)."""
         if device is None:
             device = next(model.parameters()).device
         img = noise if noise is not None else th.randn(*shape, device=device)
         for i in list(range(self.num_timesteps))[::-1]:
             t = th.tensor([i] * shape[0], device=device)
             with th.no_grad():
-                img = self.ddim_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
-                                       cond_fn=cond_fn, model_kwargs=model_kwargs, eta=eta)["sample"]
-        return img
+                out = self.ddim_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                       cond_fn=cond_fn, model_kwargs=model_kwargs, eta=eta)
+                yield out
+                img = out["sample"]
+
+    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                         model_kwargs=None, device=None, progress=False, eta=0.0):
+        """Reference :763-797."""
+        final = None
+        for sample in self.ddim_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised,
+                                                        denoised_fn=denoised_fn, cond_fn=cond_fn,
+                                                        model_kwargs=model_kwargs, device=device, progress=progress,
+                                                        eta=eta):
+            final = sample
+        return final["sample"]
 
 
 def _ops_of(model):
