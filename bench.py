@@ -356,11 +356,12 @@ def run_ours(args):
             "roofline": roof,
             "batched": batched,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and args.torch_eager:      # opt-in, informational: the oracle restatement run eagerly on the GPU
             try:
                 line["torch_eager_b200"] = torch_eager_gpu_steps(dev)
-            except Exception as e:  # noqa: BLE001 - informational only
+            except Exception as e:  # noqa: BLE001
                 line["torch_eager_b200"] = {"error": repr(e)[:200]}
+        if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_steps(2, 1, budget_s=60.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
@@ -434,6 +435,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--batch", type=int, default=8, help="extra throughput leg: edits per GPU advanced as one batch (0/1 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-eager", action="store_true",
+                    help="also time the oracle restatement (stock torch ops, fp32) eagerly on the GPU: an informational "
+                         "comparator, 14.5 steps/s on B200 (profiles/r01_bench_n1_latest.json)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
