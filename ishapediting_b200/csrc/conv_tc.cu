@@ -1157,6 +1157,8 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
     if (d->Cout < 128) bn = d->Cout;                                  // 32,64,96
     else if (d->Cout % 128 != 0 && d->Cout <= 256) bn = d->Cout;      // e.g. 192: one exact tile
     else bn = ((d->ksize == 1 || mtiles <= 2) && d->Cout % 64 == 0) ? 64 : 128;   // 1x1 / tiny images: 64-wide
+    if (bn == 64 && d->Cout % 128 == 0 && static_cast<long long>(mtiles) * (d->Cout / 64) > 2LL * sms)
+      bn = 128;       // already more 64-wide tiles than two waves (batched launches): wider tiles re-read A less
   }
   ISB_CHECK_ARG(bn >= 32 && bn <= 256 && bn % 32 == 0, "conv_tc: block_n=%d must be a multiple of 32 in [32,256]", bn);
   p.block_n = bn;

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--warm", action="store_true", help="one weight copy: weights stay L2-resident")
     ap.add_argument("--auto-only", action="store_true")
     ap.add_argument("--big", action="store_true")
+    ap.add_argument("--batch", type=int, default=1, help="images per launch (throughput mode: 8)")
     args = ap.parse_args()
     ops = CudaOps(torch.device("cuda", 0), "bf16")
     dev = ops.device
@@ -61,13 +62,13 @@ def main():
         ncopies = max(4, min(64, int(400e6 // wbytes)))           # ring > L2 (126 MB) when weights are big
         if args.warm:
             ncopies = 1
-        a = torch.randn(1, H, H, Cin, device=dev).to(torch.bfloat16)
-        out = torch.empty(1, H, H, Cout, device=dev)
+        a = torch.randn(args.batch, H, H, Cin, device=dev).to(torch.bfloat16)
+        out = torch.empty(args.batch, H, H, Cout, device=dev)
         bias = torch.randn(Cout, device=dev)
         base = [torch.randn(Cout, K, device=dev).to(torch.bfloat16) for _ in range(ncopies)]
         if args.warm:
             base = base * 16
-        flops = 2.0 * H * H * Cout * K
+        flops = 2.0 * args.batch * H * H * Cout * K
         rows = []
         bns = [64, 128, 256] if Cout % 256 == 0 else [64, 128]
         splits = [1, 2, 4, 8]
@@ -80,7 +81,7 @@ def main():
             t, err = bench(ops, a, base, bias, k, out, {"block_n": bn, "split_k": sp, "stages": stg}, False)
             if t is not None:
                 rows.append((t, bn, sp, stg))
-        if H >= 32 and Cout % 128 == 0:      # CTA-pair kernel (cta_group::2)
+        if H * H * args.batch >= 1024 and Cout % 128 == 0:      # CTA-pair kernel (cta_group::2)
             for bn in ([128, 256] if Cout % 256 == 0 else [128]):
                 for stg in (4, 5, 6):
                     t, err = bench(ops, a, base, bias, k, out, {"block_n": bn, "split_k": 1, "stages": stg, "two_cta": 1}, False)
