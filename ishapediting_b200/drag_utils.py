@@ -390,6 +390,97 @@ class HostStepPipeline:
         return self.img_host[s], self.loss_host[s]
 
 
+class ReconStepper:
+    """The loop body of train_triplane (drag_utils.py:445-463) without torch.autograd, as one static launch sequence
+    (optionally a CUDA graph): UNet forward (whole network) -> fused posterior (pred_xstart, sample, variance) ->
+    triplane decoder at the sample points -> BCE gradient -> decoder backward into the planes -> clamp / eps chain rule
+    -> UNet input-gradient backward from the OUTPUT layer -> img <- sample + variance * scale * grad.
+    Same arithmetic as recon_guided_step (which goes through the autograd bridge and launches eagerly)."""
+
+    def __init__(self, model, diffusion, decoder, n_points, scale=600.0, rng=1.0, middle=0.0, clip_denoised=True,
+                 use_graph=True):
+        self.model, self.diffusion, self.decoder = model, diffusion, decoder
+        C, R = model.in_channels, model.image_size
+        assert C == 96, "the triplane decoder reads 3 planes x 32 features"
+        self.plan = model.plan(1, R, R, want_backward=True)
+        ops = self.ops = self.plan.ops
+        dev = ops.device
+        self.scale, self.clip, self.rng, self.middle, self.P, self.R = float(scale), clip_denoised, rng, middle, n_points, R
+        self.weights = decoder.mlp_weights()
+        e = ops.empty
+        self.img, self.noise, self.grad = e((1, C, R, R)), e((1, C, R, R)), e((1, C, R, R))
+        self.sample, self.variance, self.x0 = e((1, C, R, R)), e((1, C, R, R)), e((1, C, R, R))
+        self.g_out = ops.zeros((1, 2 * C, R, R))             # d loss / d model_output: eps half only
+        self.coords, self.gt = e((n_points, 3)), e((n_points, 1))
+        self.logits, self.d_logits = e((n_points,)), e((n_points,))
+        self.planes_hwc, self.d_planes_hwc = e((3, R, R, 32)), e((3, R, R, 32))
+        self.g_x0 = e((3, 32, R, R))
+        self.loss = ops.zeros((1,))
+        self.coef = e((8,))
+        self.coef_table = diffusion.coef_table(dev, guide_scale=self.scale)
+        tmap = getattr(diffusion, "timestep_map", list(range(diffusion.num_timesteps)))
+        self.t_table = th.tensor(tmap, device=dev, dtype=th.int64)
+        self.use_graph = use_graph and dev.type == "cuda"
+        self._graph, self._warm = None, 0
+        self._cap_stream = th.cuda.Stream(device=dev) if dev.type == "cuda" else None
+
+    def _body(self):
+        plan, ops = self.plan, self.ops
+        plan.forward(self.img, plan.t_dev, -1)
+        ops.ddpm_step(self.img, plan.out_nhwc, self.coef, self.clip, noise=self.noise, sample=self.sample,
+                      var=self.variance, x0=self.x0)
+        planes = self.x0.reshape(3, 32, self.R, self.R)
+        if not (self.rng == 1.0 and self.middle == 0.0):
+            planes = planes * self.rng + self.middle
+        ops.to_nhwc(planes.contiguous(), self.planes_hwc)
+        ops.decode_points(self.planes_hwc, self.weights, self.coords, self.logits)
+        # loss = -BCEWithLogits(mean):  d loss / d logit = -(sigmoid(logit) - gt) / P
+        th.sigmoid(self.logits, out=self.d_logits)
+        self.d_logits.sub_(self.gt.reshape(-1)).mul_(-1.0 / self.P)
+        self.loss.copy_(-F.binary_cross_entropy_with_logits(self.logits, self.gt.reshape(-1)).reshape(1))
+        self.d_planes_hwc.zero_()
+        ops.decode_points_backward(self.planes_hwc, self.weights, self.coords, self.d_logits, self.d_planes_hwc)
+        ops.to_nchw(self.d_planes_hwc, self.g_x0)
+        g_x0 = self.g_x0.reshape(1, 96, self.R, self.R)
+        if not (self.rng == 1.0 and self.middle == 0.0):
+            g_x0 = g_x0 * self.rng
+        if self.clip:                                        # x0 = clamp(c0 x - c1 eps): no gradient where it saturates
+            g_x0 = g_x0 * (self.x0.abs() < 1.0)
+        self.g_out[:, :96].copy_(g_x0 * (-self.coef[1]))     # d x0 / d eps = -sqrt(1/abar - 1)
+        plan.begin_backward()
+        plan.backward_out_layer(self.g_out)
+        plan.backward(self.grad)
+        self.grad.add_(g_x0 * self.coef[0])                  # d x0 / d x = sqrt(1/abar)
+        ops.ddpm_step(self.img, plan.out_nhwc, self.coef, self.clip, noise=self.noise, grad=self.grad, x_next=self.sample)
+        self.img.copy_(self.sample)
+
+    def step(self, i, coords, gt, noise=None):
+        """Advance self.img from respaced step i to i-1 under the occupancy samples (coords (P,3), gt (P,1))."""
+        self.coef.copy_(self.coef_table[i])
+        self.plan.t_dev.copy_(self.t_table[i:i + 1])
+        self.coords.copy_(coords)
+        self.gt.copy_(gt.reshape(self.P, 1))
+        if noise is None:
+            self.noise.normal_()
+        else:
+            self.noise.copy_(noise)
+        if not self.use_graph:
+            self._body()
+            return
+        if self._graph is None:
+            if self._warm < 1:
+                self._warm += 1
+                self._body()
+                return
+            keep = self.img.clone()
+            g = th.cuda.CUDAGraph()
+            with th.cuda.graph(g, stream=self._cap_stream):
+                self._body()
+            self._graph = g
+            self.img.copy_(keep)
+        self._graph.replay()
+
+
 def recon_guided_step(model, diffusion, decoder, img, i, coords, gt, scale=600.0, noise=None, rng=1.0, middle=0.0):
     """One iteration of the reference's real-shape reconstruction guidance (drag_utils.py:445-463, SURVEY.md §8f
     rank 2): classifier guidance on the predicted x_start through the triplane decoder.  img (1,96,R,R) latent at
@@ -574,11 +665,16 @@ class DragStuff:
             occ = th.as_tensor(np.asarray(occupancies), dtype=th.float32).reshape(-1, 1)
             g = th.Generator().manual_seed(seed) if seed is not None else None
             R = self.args.image_size
-            img = th.randn((1, 96, R, R), generator=g).to(self.device)
+            n = min(batch_size, pts.shape[0])
+            st = ReconStepper(self.model, self.diffusion, self.decoder, n, scale=scale, rng=self.range,
+                              middle=self.middle, use_graph=self.use_graph)
+            st.img.copy_(th.randn((1, 96, R, R), generator=g).to(self.device))
+            pts_d, occ_d = pts.to(self.device), occ.to(self.device)
             for i in range(self.args.num_steps - 1, -1, -1):
-                idx = th.randperm(pts.shape[0], generator=g)[:batch_size]     # DataLoader(shuffle=True) batch, :442,454
+                idx = th.randperm(pts.shape[0], generator=g)[:n].to(self.device)   # DataLoader(shuffle=True) batch, :442,454
                 noise = th.randn((1, 96, R, R), generator=g).to(self.device)
-                img, _ = self.recon_guided_step(img, i, pts[idx], occ[idx], scale=scale, noise=noise)
+                st.step(i, pts_d[idx], occ_d[idx], noise=noise)
+            img = st.img.clone()
         self.clear_params()
         self.mesh = self.get_mesh(tri_feat=img)
         self.mesh0 = copy.deepcopy(self.mesh) if not th.is_tensor(self.mesh) else self.mesh.clone()

@@ -137,3 +137,13 @@ def test_recon_guided_step(mode, tol):
     print("recon", mode, {"img": err, "loss": abs(float(loss) - float(ref["loss"]))})
     assert err < tol
     assert abs(float(loss) - float(ref["loss"])) < (1e-4 if mode == "fp32" else 2e-2)
+    # the same step as a static launch sequence: eager warm-up, graph capture, replay
+    from ishapediting_b200.drag_utils import ReconStepper
+
+    st = ReconStepper(model, diff, dec, coords.shape[0], scale=600.0, use_graph=True)
+    for rep in range(3):
+        st.img.copy_(x.to(DEV))
+        st.step(120, coords.to(DEV), gt.to(DEV), noise=noise.to(DEV))
+        e2 = rel_l2(st.img, ref["img"])
+        assert e2 < tol, (rep, e2)
+        assert abs(float(st.loss) - float(ref["loss"])) < (1e-4 if mode == "fp32" else 2e-2)

@@ -132,6 +132,13 @@ def test_recon_guided_step_matches_oracle():
     x, noise, coords, gt = recon_inputs(cfg["image_size"], n_pts=500)
     ref = O.recon_guided_step(sd, cfg, sched, x, 120, noise, w, coords, gt, scale=600.0)
     nxt, loss = recon_guided_step(model, diff, dec, x, 120, coords, gt, scale=600.0, noise=noise)
+    # the graph-less static schedule (ReconStepper) is the same arithmetic without torch.autograd
+    from ishapediting_b200.drag_utils import ReconStepper
+
+    st = ReconStepper(model, diff, dec, coords.shape[0], scale=600.0, use_graph=False)
+    st.img.copy_(x)
+    st.step(120, coords, gt, noise=noise)
+    assert rel_l2(st.img, nxt) < 2e-4 and abs(float(st.loss) - float(loss)) < 1e-5
     # The decoder gradient is ill-conditioned in fp32 (sin/cos of ~50 rad arguments, ReLU masks, few points): the
     # ORACLE's own gradient moves by 0.8 % when its planes are perturbed by 1e-6 relative, and by 0.14 % between fp32
     # and fp64.  The two sides agree on pred_xstart to 7e-7, hence on the gradient to ~1 % and on the next latent

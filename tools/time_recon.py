@@ -37,6 +37,19 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     print(f"recon-guided step ({args.mode}, eager, 40000 points): {e0.elapsed_time(e1) / reps:.2f} ms  loss {float(loss):.4f}")
+    from ishapediting_b200.drag_utils import ReconStepper
+
+    st = ReconStepper(model, diff, dec, 40000, scale=600.0, use_graph=True)
+    st.img.copy_(img)
+    for k in range(3):
+        st.step(185 - k, pts, occ, noise=noise)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(20):
+        st.step(180 - k, pts, occ, noise=noise)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"recon-guided step ({args.mode}, ReconStepper, CUDA graph): {e0.elapsed_time(e1) / 20:.2f} ms  loss {float(st.loss):.4f}")
     # decoder kernels alone
     e0.record()
     for _ in range(20):
