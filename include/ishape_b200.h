@@ -210,10 +210,11 @@ int isb_attention_flash_backward(const void* qkv, const void* out, const void* d
 /* film_all[n, :] = W_all @ silu(W2 @ silu(W1 @ sinus(t[n]) + b1) + b2) + b_all
  * where W_all/b_all is the row-concatenation of every ResBlock's emb_layers
  * Linear (rows_all = sum 2*Cout).  All weights fp32 row-major [out,in].
- * t is a device int64 array of ORIGINAL timesteps (after respace.py:122-126);
+ * t is a device fp32 array of the timestep VALUES the UNet sees (after respace.py:122-126 and, with
+ * rescale_timesteps, gaussian_diffusion.py:171-174: possibly fractional — the reference embeds floats, nn.py:116);
  * freqs [model_ch/2] is the reference's exp(-ln(1e4)*i/half) table (nn.py:113-115)
  * computed once by the host.  scratch: N * (model_ch + 2*hidden) floats. */
-int isb_time_embed(const int64_t* t, const float* freqs, int N, int model_ch,
+int isb_time_embed(const float* t, const float* freqs, int N, int model_ch,
                    int hidden, const float* w1, const float* b1, const float* w2,
                    const float* b2, const float* w_all, const float* b_all,
                    int rows_all, float* scratch, float* film_all,

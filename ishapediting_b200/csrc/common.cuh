@@ -62,8 +62,9 @@ tensormap_encode_fn get_tensormap_encode();
 // Programmatic dependent launch (PDL).  Every kernel of this library is launched with
 // programmaticStreamSerialization: it may be scheduled while its predecessor in the stream is
 // still draining, runs its input-independent prologue, and blocks in pdl_wait() until the
-// predecessor has completed and flushed.  pdl_trigger() (first statement of every kernel) lets the
-// successor start that early.  Rule: no global read of produced data and NO global write before
+// predecessor has completed and flushed.  pdl_trigger() lets the successor start that early: the conv kernels
+// issue it as their first statement (their successors have a real input-independent prologue); every other kernel
+// issues pdl_wait() FIRST and pdl_trigger() right after it, so that waiting grids never cascade.  Rule: no global read of produced data and NO global write before
 // pdl_wait().  ISB_PDL=0 in the environment turns the attribute off (plain stream order).
 bool pdl_enabled();
 bool pdl_enabled_conv();

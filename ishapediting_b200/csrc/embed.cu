@@ -8,14 +8,14 @@ namespace isb {
 
 // emb[n, i] = cos(t*f_i) for i < half, sin(t*f_{i-half}) otherwise; freqs supplied by the host
 // (computed with the reference's own expression so the table is bit-identical).
-__global__ void sinusoid_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs, int N, int half,
+__global__ void sinusoid_kernel(const float* __restrict__ t, const float* __restrict__ freqs, int N, int half,
                                 float* __restrict__ emb) {
   pdl_wait();      // predecessor complete and flushed
   pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * half) return;
   const int n = idx / half, i = idx % half;
-  const float arg = static_cast<float>(t[n]) * freqs[i];
+  const float arg = t[n] * freqs[i];     // timesteps[:, None].float() * freqs[None]  (nn.py:116)
   emb[n * 2 * half + i] = cosf(arg);
   emb[n * 2 * half + half + i] = sinf(arg);
 }
@@ -52,7 +52,7 @@ gemv_rows_kernel(const float* __restrict__ W, const float* __restrict__ b, const
 
 extern "C" {
 
-int isb_time_embed(const int64_t* t, const float* freqs, int N, int model_ch, int hidden, const float* w1,
+int isb_time_embed(const float* t, const float* freqs, int N, int model_ch, int hidden, const float* w1,
                    const float* b1, const float* w2, const float* b2, const float* w_all, const float* b_all,
                    int rows_all, float* scratch, float* film_all, isb_stream_t stream) {
   ISB_CHECK_ARG(t && freqs && w1 && b1 && w2 && b2 && w_all && b_all && scratch && film_all, "isb_time_embed: null pointer");

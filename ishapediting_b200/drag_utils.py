@@ -186,6 +186,7 @@ class GuidedStepper:
         B = self.batch = len(geos)
         assert all(g.npts == geos[0].npts and g.group_size == geos[0].group_size for g in geos)
         self.plan = model.plan(B, model.image_size, model.image_size, want_backward=True)
+        self.weights_generation = model.weights_generation      # the plan's weight panels are packed copies
         ops = self.ops = self.plan.ops
         dev = ops.device
         self.feat_layer, self.cof, self.scale, self.clip = feat_layer, float(cof), float(scale), clip_denoised
@@ -235,8 +236,10 @@ class GuidedStepper:
 
     def compatible(self, geometry, cof, loss_type):
         """True if a new edit (other handles/targets, other scale) can reuse this stepper and its captured graph:
+        the model's weights are still the ones this stepper's plan packed (load_state_dict / convert_to_fp16 / .to()
+        on the same model object make it stale — the reference swaps checkpoints that way, drag_utils.py:229-232),
         same number of sample points and the by-value kernel scalars (cof, loss type) unchanged."""
-        return (geometry.npts == self.geo.npts and geometry.group_size == self.geo.group_size
+        return (self.weights_generation == self.model.weights_generation and geometry.npts == self.geo.npts and geometry.group_size == self.geo.group_size
                 and float(cof) == self.cof and (1 if loss_type == "l1" else 0) == self.loss_type)
 
     def retarget(self, geometry, scale):
@@ -287,7 +290,7 @@ class GuidedStepper:
         if overlap:
             th.cuda.current_stream().wait_event(self._ev_join)
         ops.ddpm_step(self.img, plan.out_nhwc, self.coef, self.clip, noise=self.noise, grad=self.grad,
-                      x_next=self.img_next, sample=self.sample, var=self.variance)
+                      x_next=self.img_next, sample=self.sample, var=self.variance, model_out_nhwc=True)
         self.img.copy_(self.img_next)
 
     def step(self, i, origin_feature, noise=None):
@@ -405,7 +408,13 @@ class ReconStepper:
         self.plan = model.plan(1, R, R, want_backward=True)
         ops = self.ops = self.plan.ops
         dev = ops.device
-        self.scale, self.clip, self.rng, self.middle, self.P, self.R = float(scale), clip_denoised, rng, middle, n_points, R
+        self.scale, self.clip, self.P, self.R = float(scale), clip_denoised, n_points, R
+        # range / middle: scalars, or the per-channel (1,96,1,1) statistics of explicit_normalization
+        # (drag_utils.py:236-245); decided once, applied at (1,96,R,R) BEFORE the (3,32,R,R) reshape like get_mesh
+        self.identity_norm = (not th.is_tensor(rng) and not th.is_tensor(middle) and float(rng) == 1.0
+                              and float(middle) == 0.0)
+        as_dev = lambda v: v.to(device=dev, dtype=th.float32) if th.is_tensor(v) else float(v)  # noqa: E731
+        self.rng, self.middle = as_dev(rng), as_dev(middle)
         self.weights = decoder.mlp_weights()
         e = ops.empty
         self.img, self.noise, self.grad = e((1, C, R, R)), e((1, C, R, R)), e((1, C, R, R))
@@ -428,11 +437,9 @@ class ReconStepper:
         plan, ops = self.plan, self.ops
         plan.forward(self.img, plan.t_dev, -1)
         ops.ddpm_step(self.img, plan.out_nhwc, self.coef, self.clip, noise=self.noise, sample=self.sample,
-                      var=self.variance, x0=self.x0)
-        planes = self.x0.reshape(3, 32, self.R, self.R)
-        if not (self.rng == 1.0 and self.middle == 0.0):
-            planes = planes * self.rng + self.middle
-        ops.to_nhwc(planes.contiguous(), self.planes_hwc)
+                      var=self.variance, x0=self.x0, model_out_nhwc=True)
+        planes = self.x0 if self.identity_norm else self.x0 * self.rng + self.middle      # (1,96,R,R)
+        ops.to_nhwc(planes.reshape(3, 32, self.R, self.R).contiguous(), self.planes_hwc)
         ops.decode_points(self.planes_hwc, self.weights, self.coords, self.logits)
         # loss = -BCEWithLogits(mean):  d loss / d logit = -(sigmoid(logit) - gt) / P
         th.sigmoid(self.logits, out=self.d_logits)
@@ -442,7 +449,7 @@ class ReconStepper:
         ops.decode_points_backward(self.planes_hwc, self.weights, self.coords, self.d_logits, self.d_planes_hwc)
         ops.to_nchw(self.d_planes_hwc, self.g_x0)
         g_x0 = self.g_x0.reshape(1, 96, self.R, self.R)
-        if not (self.rng == 1.0 and self.middle == 0.0):
+        if not self.identity_norm:
             g_x0 = g_x0 * self.rng
         if self.clip:                                        # x0 = clamp(c0 x - c1 eps): no gradient where it saturates
             g_x0 = g_x0 * (self.x0.abs() < 1.0)
@@ -451,7 +458,8 @@ class ReconStepper:
         plan.backward_out_layer(self.g_out)
         plan.backward(self.grad)
         self.grad.add_(g_x0 * self.coef[0])                  # d x0 / d x = sqrt(1/abar)
-        ops.ddpm_step(self.img, plan.out_nhwc, self.coef, self.clip, noise=self.noise, grad=self.grad, x_next=self.sample)
+        ops.ddpm_step(self.img, plan.out_nhwc, self.coef, self.clip, noise=self.noise, grad=self.grad, x_next=self.sample,
+                      model_out_nhwc=True)
         self.img.copy_(self.sample)
 
     def step(self, i, coords, gt, noise=None):
@@ -575,7 +583,7 @@ class DragStuff:
         def body():
             plan.forward(st["img"], plan.t_dev, feat_layer)
             ops.ddpm_step(st["img"], plan.out_nhwc, st["coef"], self.args.clip_denoised, noise=st["noise"],
-                          x_next=st["next"])
+                          x_next=st["next"], model_out_nhwc=True)
 
         use_graph = self.use_graph and dev.type == "cuda" and st["feat_layer"] == feat_layer
         if not use_graph:

@@ -366,7 +366,7 @@ class _Plan:
         hidden = self.te_w1.shape[0]
         self.te_scratch = ops.empty((N * (mc + 2 * hidden),))
         self.film_all = ops.empty((N, self.film_rows))
-        self.t_dev = ops.zeros((N,), th.int64)
+        self.t_dev = ops.zeros((N,), th.float32)     # timestep values as the reference embeds them: floats (nn.py:116)
 
         # --- input conv (input_blocks[0], unet.py:482) ---
         conv0 = model.input_blocks[0][0]
@@ -444,7 +444,7 @@ class _Plan:
 
     # -- forward ----------------------------------------------------------------------------------
     def forward(self, x_nchw, t_orig, feat_layer=-1, upto_feat_only=False):
-        """x_nchw fp32 [N,C,H,W] (device), t_orig int64 [N] original timesteps (device).
+        """x_nchw fp32 [N,C,H,W] (device), t_orig fp32 [N] timestep values (device).
         Fills self.out_nhwc (unless upto_feat_only) and returns the inter-feature _T (or None)."""
         ops = self.ops
         self.generation += 1
@@ -652,6 +652,7 @@ class UNetModel(nn.Module):
         self._plans = {}
         self._ops = None
         self._mode = "bf16" if use_fp16 else "fp32"
+        self.weights_generation = 0      # bumped whenever packed weight panels (plans) become stale
 
     # -- precision / backend selection ------------------------------------------------------------
     def convert_to_fp16(self):
@@ -673,7 +674,10 @@ class UNetModel(nn.Module):
         self.invalidate()
 
     def invalidate(self):
+        """Parameters, precision mode or backend changed: drop every plan (their weight panels are packed COPIES) and
+        tell whoever cached one (GuidedStepper and its captured graph, FiLM rows) through `weights_generation`."""
         self._plans = {}
+        self.weights_generation = getattr(self, "weights_generation", 0) + 1
 
     def load_state_dict(self, *a, **kw):
         r = super().load_state_dict(*a, **kw)
@@ -713,7 +717,7 @@ class UNetModel(nn.Module):
         N, _, H, W = x.shape
         need_grad = th.is_grad_enabled() and x.requires_grad
         plan = self.plan(N, H, W, want_backward=True)
-        t_orig = timesteps.to(device=x.device, dtype=th.int64).contiguous()
+        t_orig = timesteps.to(device=x.device, dtype=th.float32).contiguous()   # may be fractional (rescale_timesteps)
         if need_grad:
             return _UNetFn.apply(x, self, plan, t_orig, feat_layer)
         with th.no_grad():

@@ -62,6 +62,10 @@ class CudaOps:
         self._ws_slot = 0
         self._bg = False
         self._gn_scratch = {}
+        # Buffers that were handed to launches and later outgrown.  Captured CUDA graphs keep RAW pointers into them
+        # (GuidedStepper / ReconStepper / the no-grad step graph share this ops object per model), and their arrival
+        # counters must stay 0 between launches, so they are never returned to the caching allocator.
+        self._retired = []
 
     # ---- memory -----------------------------------------------------------
     def empty(self, shape, dtype=torch.float32):
@@ -81,6 +85,8 @@ class CudaOps:
         if ws is None or ws.numel() < nbytes:
             if torch.cuda.is_current_stream_capturing():
                 raise _lib.IsbError("conv workspace must be sized by an eager warm-up before graph capture")
+            if ws is not None:
+                self._retired.append(ws)      # graphs captured earlier still point at it
             # zero-filled: the split-K arrival counters at its head must start (and are left) at 0
             ws = torch.zeros(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
@@ -113,6 +119,10 @@ class CudaOps:
         need = N * groups
         cur = self._gn_scratch.get(which)
         if cur is None or cur[1] < need:
+            if torch.cuda.is_current_stream_capturing():
+                raise _lib.IsbError("GroupNorm scratch must be sized by an eager warm-up before graph capture")
+            if cur is not None:
+                self._retired.append(cur[0])  # graphs captured at a smaller batch still point at it
             nbytes = self.lib.isb_gn_scratch_bytes(N, groups)
             cur = (torch.zeros(nbytes, dtype=torch.uint8, device=self.device), need)
             self._gn_scratch[which] = cur
@@ -326,7 +336,7 @@ class CudaOps:
 
     # ---- timestep embedding ---------------------------------------------------------
     def time_embed(self, t, freqs, w1, b1, w2, b2, w_all, b_all, scratch, film_all):
-        _chk(t, torch.int64)
+        _chk(t, torch.float32)
         N = t.shape[0]
         model_ch, hidden = w1.shape[1], w1.shape[0]
         assert scratch.numel() >= N * (model_ch + 2 * hidden)
@@ -337,15 +347,22 @@ class CudaOps:
 
     # ---- DDPM update -------------------------------------------------------------------
     def ddpm_step(self, x, model_out, coef, clip_denoised, noise=None, grad=None, x_next=None, sample=None, mean=None,
-                  var=None, x0=None, eps=None):
+                  var=None, x0=None, eps=None, *, model_out_nhwc=False):
+        """model_out: the UNet output (eps | v).  Its layout is stated by the caller, never guessed from the shape:
+        NCHW [N,2C,H,W] (what UNetModel.forward returns) by default, `model_out_nhwc=True` for the plan's own
+        channels-last buffer [N,H,W,>=2C]."""
         _chk(x, torch.float32); _chk(model_out, torch.float32); _chk(coef, torch.float32)
         N, Cc, H, W = x.shape
         d = _lib.DdpmDesc()
         d.x, d.model_out = _p(x), _p(model_out)
-        if model_out.shape[1] == 2 * Cc and model_out.shape[2:] == x.shape[2:]:
-            d.model_out_nchw, d.model_out_cstride = 1, 0
-        else:
+        if model_out_nhwc:
+            assert tuple(model_out.shape[:3]) == (N, H, W) and model_out.shape[3] >= 2 * Cc, \
+                f"NHWC model output {tuple(model_out.shape)} does not match x {tuple(x.shape)}"
             d.model_out_nchw, d.model_out_cstride = 0, model_out.shape[3]
+        else:
+            assert tuple(model_out.shape) == (N, 2 * Cc, H, W), \
+                f"NCHW model output {tuple(model_out.shape)} does not match x {tuple(x.shape)}"
+            d.model_out_nchw, d.model_out_cstride = 1, 0
         d.noise, d.grad, d.coef = _p(noise), _p(grad), _p(coef)
         d.N, d.C, d.H, d.W, d.clip_denoised = N, Cc, H, W, int(clip_denoised)
         d.x_next, d.sample, d.mean, d.var, d.x0, d.eps = _p(x_next), _p(sample), _p(mean), _p(var), _p(x0), _p(eps)

@@ -252,9 +252,9 @@ class RefOps:
 
     # ---- DDPM ----
     def ddpm_step(self, x, model_out, coef, clip_denoised, noise=None, grad=None, x_next=None, sample=None, mean=None,
-                  var=None, x0=None, eps=None):
+                  var=None, x0=None, eps=None, *, model_out_nhwc=False):
         C = x.shape[1]
-        mo = model_out if (model_out.shape[1] == 2 * C and model_out.shape[2:] == x.shape[2:]) else _nchw(model_out)
+        mo = _nchw(model_out) if model_out_nhwc else model_out
         e, v = mo[:, :C], mo[:, C:2 * C]
         c = coef if coef.dim() == 1 else [coef[:, k].reshape(-1, 1, 1, 1) for k in range(8)]
         frac = (v + 1) / 2

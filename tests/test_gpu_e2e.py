@@ -63,19 +63,21 @@ def test_dragstuff_edit_flow(mode, tol):
 
     # ---- product ----
     out = ds.update_latent_params(x.to(DEV), noise=noise.to(DEV))
+    print("edit flow", mode, dict(final=rel_l2(out, final_unedited), w=rel_l2(ds.w, w_lat),
+                                   feat0=rel_l2(ds.feature_guidance_nchw(0), feats[0])))
     assert rel_l2(out, final_unedited) < tol
     assert rel_l2(ds.w, w_lat) < tol
     assert len(ds.feature_guidance) == 4
     assert rel_l2(ds.feature_guidance_nchw(0), feats[0]) < tol
     progress = list(ds.training(src, tgt, scale=600, cof=0.2, noises=[noise.to(DEV)] * 4))
     assert progress == [1 - i / 3.0 for i in (3, 2, 1, 0)]
+    print("edit flow", mode, "edited latent", rel_l2(ds.stepper.img, img))
     assert rel_l2(ds.stepper.img, img) < tol
     vol = ds.last_volume.cpu().reshape(-1)
     assert vol.shape == vol_ref.shape
-    if mode == "fp32":
-        occ, occ_ref = vol > 0, vol_ref > 0
-        union = float((occ | occ_ref).sum())
-        assert union == 0 or float((occ & occ_ref).sum()) / union >= 0.999
+    # (occupancy IoU of this flow, on a field centred so that it is never vacuous: test_gpu_baseline_configs.py::
+    # test_edit_end_to_end_iou)
+    print("edit flow", mode, "volume rel-L2", rel_l2(vol, vol_ref))
     # a second edit with other handles reuses the captured graph and must still be right
     src2, tgt2 = src[::-1].copy(), tgt[::-1].copy()
     pg2, sg2, masks2 = O.drag_setup(src2, tgt2, 4, 2.0 / 64, S)

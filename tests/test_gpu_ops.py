@@ -214,7 +214,7 @@ def test_attention_flash_forward_backward(ops, ref, N, S, heads):
 def test_time_embed(ops, ref):
     g = G(7)
     mc, hid, rows, N = 64, 256, 1000, 3
-    t = torch.tensor([0, 246, 999])
+    t = torch.tensor([0.0, 246.0, 997.5])      # fractional values occur with rescale_timesteps (gaussian_diffusion.py:171-174)
     from ishapediting_b200.guided_diffusion.nn import timestep_freqs
 
     freqs = timestep_freqs(mc)
@@ -241,7 +241,8 @@ def test_ddpm_step(ops, ref, nchw):
     for name, o in (("ref", ref), ("cuda", ops)):
         dev = "cpu" if name == "ref" else DEV
         outs = {k: torch.zeros(N, C, H, W, device=dev) for k in names}
-        o.ddpm_step(x.to(dev), mo.to(dev), coef.to(dev), True, noise=noise.to(dev), grad=grad.to(dev), **outs)
+        o.ddpm_step(x.to(dev), mo.to(dev), coef.to(dev), True, noise=noise.to(dev), grad=grad.to(dev),
+                    model_out_nhwc=not nchw, **outs)
         r[name] = outs
     for k in names:
         assert rel_l2(r["cuda"][k], r["ref"][k]) < 1e-5, k
@@ -251,7 +252,8 @@ def test_ddpm_step(ops, ref, nchw):
     for name, o in (("ref", ref), ("cuda", ops)):
         dev = "cpu" if name == "ref" else DEV
         outs = {k: torch.zeros(N, C, H, W, device=dev) for k in names}
-        o.ddpm_step(x.to(dev), mo.to(dev), coef2.to(dev), True, noise=noise.to(dev), grad=grad.to(dev), **outs)
+        o.ddpm_step(x.to(dev), mo.to(dev), coef2.to(dev), True, noise=noise.to(dev), grad=grad.to(dev),
+                    model_out_nhwc=not nchw, **outs)
         r2[name] = outs
     for k in names:
         assert rel_l2(r2["cuda"][k], r2["ref"][k]) < 1e-5, k

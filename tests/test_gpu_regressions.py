@@ -1,0 +1,145 @@
+"""Regression tests for lifetime / staleness bugs on the GPU path (round-1 advisor findings)."""
+import pytest
+import torch
+
+from oracle import nfd_oracle as O
+from tests.conftest import rel_l2
+from tests.helpers import build_decoder, build_model, drag_problem, recon_inputs, seeded_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _stepper_case(mode="bf16"):
+    from ishapediting_b200.drag_utils import DragGeometry, GuidedStepper
+
+    cfg = O.mid_cfg()
+    sd = O.synth_state_dict(cfg)
+    model, diff = build_model(cfg, sd, mode, DEV)
+    sched = O.Schedule(cfg["diffusion_steps"], cfg["timestep_respacing"])
+    g, x, x2, noise = seeded_inputs(cfg)
+    origin, src, tgt, r1, voxel, pg, sg, masks = drag_problem(cfg, sd, sched, x2, noise, 49, g, r1=4, voxel=2.0 / 64)
+    geo = DragGeometry(src, tgt, r1, voxel, origin.shape[-1], origin.shape[1])
+    st = GuidedStepper(model, diff, geo, cfg["feat_layer"], 0.2, "l2", 600.0, use_graph=True)
+    origin_d = origin.permute(0, 2, 3, 1).contiguous().to(DEV)
+    return cfg, sd, model, diff, st, x.to(DEV), origin_d, noise.to(DEV), (src, tgt, r1, voxel)
+
+
+def test_captured_graph_survives_a_larger_batch_plan():
+    """A graph captured at batch 1 keeps raw pointers to the shared GroupNorm scratch / split-K workspace.  A later
+    batch-8 pass (ddpm_inversion(batch=8), a batch-8 stepper) outgrows those buffers; the batch-1 graph must still
+    replay correctly afterwards (the outgrown buffers are retired, never freed)."""
+    cfg, sd, model, diff, st, x, origin, noise, _ = _stepper_case()
+    for _ in range(3):                      # warm-up, capture, replay
+        st.img.copy_(x)
+        st.step(49, origin, noise)
+    want_img, want_grad = st.img.clone(), st.grad.clone()
+    assert st._graph is not None
+    # batch-8 work on the same model / ops object: forward + backward through the autograd bridge, then garbage
+    # allocations that would land in any freed block
+    x8 = torch.randn(8, x.shape[1], x.shape[2], x.shape[3], device=DEV, requires_grad=True)
+    out8, feat8 = model(x8, torch.full((8,), 246, device=DEV), feat_layer=cfg["feat_layer"])
+    (feat8.sum() + out8.sum()).backward()
+    with torch.no_grad():
+        diff.ddpm_inversion(model, x[:1], 8, batch=8, feat_layer=cfg["feat_layer"])
+    del x8, out8, feat8
+    torch.cuda.empty_cache()
+    junk = [torch.full((1 << 20,), float("nan"), device=DEV) for _ in range(64)]
+    st.img.copy_(x)
+    st.step(49, origin, noise)
+    torch.cuda.synchronize()
+    del junk
+    assert torch.equal(st.img, want_img) and torch.equal(st.grad, want_grad)
+    # and the shared buffers are still clean: a second replay gives the same step again
+    st.img.copy_(x)
+    st.step(49, origin, noise)
+    assert torch.equal(st.img, want_img)
+
+
+def test_stepper_is_dropped_when_weights_change():
+    """The reference swaps checkpoints with load_state_dict on the SAME model object (drag_utils.py:229-232).  The
+    cached GuidedStepper (packed weight copies, FiLM rows, captured graph) must not survive that."""
+    from ishapediting_b200.drag_utils import DragStuff, get_args
+
+    cfg = O.mid_cfg()
+    cfg.update(in_out_channels=96, timestep_respacing="20")
+    sd1 = O.synth_state_dict(cfg, seed=1234)
+    sd2 = O.synth_state_dict(cfg, seed=4321)
+    a = get_args(["--num_steps", "20", "--w_time", "3", "--shape_resolution", "16", "--feat_layer", "5", "--resolution", "32"])
+    a.channel_mult, a.attention_resolutions, a.use_fp16 = "1,2,4", "16,8", True
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 96, 32, 32, generator=g).to(DEV)
+    noise = torch.randn(1, 96, 32, 32, generator=g).to(DEV)
+    src = (torch.rand(3, 3, generator=g) - 0.5).numpy()
+    tgt = src + (torch.rand(3, 3, generator=g).numpy() - 0.5) * 0.4
+
+    def edit(ds):
+        ds.update_latent_params(x, noise=noise)
+        list(ds.training(src, tgt, scale=600, cof=0.2, noises=[noise] * 3))
+        return ds.stepper.img.clone()
+
+    def fresh(sd):
+        ds = DragStuff(args=a, device=DEV, use_graph=True)
+        ds.model.load_state_dict(sd)
+        ds.model.to(DEV).eval()
+        ds.set_offset1(4)
+        return ds
+
+    ds = fresh(sd1)
+    img1 = edit(ds)
+    gen, stepper1 = ds.model.weights_generation, ds.stepper
+    ds.model.load_state_dict(sd2)                        # checkpoint swap on the same object
+    assert ds.model.weights_generation > gen
+    img2 = edit(ds)
+    assert ds.stepper is not stepper1, "stale stepper (old weights, old graph) was reused"
+    want2 = edit(fresh(sd2))
+    assert torch.equal(img2, want2)
+    assert rel_l2(img2, img1) > 1e-3                     # the two checkpoints really differ
+    # precision switch on the same object: bf16 -> fp32 must re-plan too
+    ds.model.convert_to_fp32()
+    img3 = edit(ds)
+    assert rel_l2(img3, img2) < 2e-2 and not torch.equal(img3, img2)
+
+
+def test_recon_stepper_with_per_channel_statistics():
+    """explicit_normalization=True (the reference default) makes range / middle (1,96,1,1) tensors
+    (drag_utils.py:236-245); ReconStepper must scale at (1,96,R,R) before the (3,32,R,R) reshape."""
+    from ishapediting_b200.drag_utils import ReconStepper, recon_guided_step
+
+    cfg = O.mid_cfg()
+    cfg.update(in_out_channels=96)
+    sd = O.synth_state_dict(cfg)
+    R = cfg["image_size"]
+    model, diff = build_model(cfg, sd, "fp32", DEV)
+    dec, w, _ = build_decoder(R, DEV)
+    sched = O.Schedule(cfg["diffusion_steps"], cfg["timestep_respacing"])
+    x, noise, coords, gt = recon_inputs(R, n_pts=1500)
+    g = torch.Generator().manual_seed(3)
+    rng = (0.5 + torch.rand(1, 96, 1, 1, generator=g))
+    middle = 0.1 * torch.randn(1, 96, 1, 1, generator=g)
+    ref = O.recon_guided_step(sd, cfg, sched, x, 120, noise, w, coords, gt, scale=600.0, rng=rng, middle=middle)
+    nxt, loss = recon_guided_step(model, diff, dec, x.to(DEV), 120, coords, gt, scale=600.0, noise=noise.to(DEV),
+                                  rng=rng.to(DEV), middle=middle.to(DEV))
+    assert rel_l2(nxt, ref["img"]) < 2e-3
+    st = ReconStepper(model, diff, dec, coords.shape[0], scale=600.0, rng=rng, middle=middle, use_graph=True)
+    for rep in range(3):
+        st.img.copy_(x.to(DEV))
+        st.step(120, coords.to(DEV), gt.to(DEV), noise=noise.to(DEV))
+        assert rel_l2(st.img, ref["img"]) < 2e-3, rep
+        assert abs(float(st.loss) - float(ref["loss"])) < 1e-4
+
+
+def test_fractional_timesteps_are_embedded_as_floats():
+    """rescale_timesteps on a base process whose length does not divide 1000 feeds fractional timesteps to the UNet
+    (gaussian_diffusion.py:171-174); the reference embeds them as floats (nn.py:116)."""
+    cfg = O.mid_cfg()
+    sd = O.synth_state_dict(cfg)
+    model, _ = build_model(cfg, sd, "fp32", DEV)
+    g, x, _, _ = seeded_inputs(cfg)
+    t = torch.tensor([246.75])
+    with torch.no_grad():
+        ref = O.unet_forward(sd, cfg, x, t, -1)
+        trunc = O.unet_forward(sd, cfg, x, torch.tensor([246.0]), -1)
+        got = model(x.to(DEV), t.to(DEV))
+    assert rel_l2(got, ref) < 1e-4
+    assert rel_l2(trunc, ref) > 10 * rel_l2(got, ref)
