@@ -154,7 +154,10 @@ typedef struct isb_gn_desc {
   const float* partials; int partial_slots;
 } isb_gn_desc;
 /* scratch: device buffer of isb_gn_scratch_bytes(N, groups) bytes, must be
- * zero-initialised once by the caller and is left zeroed by each call. */
+ * zero-initialised once by the caller and is left zeroed by each call.  The
+ * arrival counters occupy a fixed 16 KiB head (N*groups <= 4096), so one buffer
+ * sized for the largest N may serve launches of every smaller N; launches that
+ * may run CONCURRENTLY (different streams) need separate buffers. */
 size_t isb_gn_scratch_bytes(int N, int groups);
 int isb_gn_forward(const isb_gn_desc* d, void* scratch, isb_stream_t stream);
 

@@ -13,6 +13,7 @@
 namespace isb {
 
 constexpr int GN_MAX_SPLITS = 64;
+constexpr int GN_MAX_NG = 4096;   // arrival counters at the head of the scratch buffer (N * groups <= 4096)
 
 struct GnArgs {
   const float* x1; const float* x2;
@@ -721,9 +722,14 @@ static int gn_fill_args(const isb_gn_desc* d, void* scratch, GnArgs* a) {
   a->silu = d->silu; a->resample = d->resample;
   a->stats = d->stats;
   const size_t ng = static_cast<size_t>(d->N) * d->groups;
+  // The arrival counters live in a FIXED-size region at the head of the scratch buffer, whatever N is: callers
+  // reuse one buffer for plans of different batch sizes, and the counters must be 0 between launches.  (With an
+  // N-dependent layout a batch-1 launch wrote its partial sums where a batch-8 launch keeps the counters of images
+  // 1..3 — the statistics of exactly those images then came out wrong.)
+  ISB_CHECK_ARG(ng <= GN_MAX_NG, "groupnorm: N*groups=%zu exceeds the %d arrival counters of the scratch layout", ng, GN_MAX_NG);
   char* s = static_cast<char*>(scratch);
   a->counters = reinterpret_cast<int*>(s);
-  size_t off = (ng * sizeof(int) + 15) & ~static_cast<size_t>(15);
+  size_t off = GN_MAX_NG * sizeof(int);
   a->partials = reinterpret_cast<double2*>(s + off);
   off += ng * GN_MAX_SPLITS * sizeof(double2);
   a->bstats = reinterpret_cast<float*>(s + off);
@@ -743,7 +749,7 @@ extern "C" {
 
 size_t isb_gn_scratch_bytes(int N, int groups) {
   const size_t ng = static_cast<size_t>(N) * groups;
-  size_t off = (ng * sizeof(int) + 15) & ~static_cast<size_t>(15);
+  size_t off = isb::GN_MAX_NG * sizeof(int);      // fixed counter region, see gn_fill_args
   off += ng * isb::GN_MAX_SPLITS * sizeof(double2);
   off += ng * 2 * sizeof(float);
   return off;

@@ -1,10 +1,11 @@
 """Import the UNMODIFIED reference modules from /root/reference as the pinning oracle.
 
 TEST INFRASTRUCTURE ONLY (see oracle/nfd_oracle.py header).  /root/reference exists only in the
-build container; on the GPU box `available()` is False and callers fall back to the committed
-fixtures under tests/golden/.  Third-party modules the reference imports at module scope but that
-are not installable offline are stubbed: mpi4py, blobfile, open3d, mcubes,
-matplotlib.  Nothing from the reference is copied; it is executed in place.
+build container; elsewhere (the GPU box) the git-ignored snapshot oracle/_ref/ made by
+oracle/build_ref.py is used, and without either `available()` is False and callers fall back to the
+committed fixtures under tests/golden/.  Third-party modules the reference imports at module scope
+but that are not installable offline are stubbed: mpi4py, blobfile, open3d, mcubes,
+matplotlib.  The reference modules are executed in place, unmodified.
 """
 from __future__ import annotations
 
@@ -12,7 +13,16 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("ISB_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    env = os.environ.get("ISB_REFERENCE_ROOT")
+    cands = [env] if env else ["/root/reference", os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if os.path.isdir(os.path.join(c, "neural_field_diffusion", "guided_diffusion")):
+            return c
+    return cands[0]
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

@@ -19,10 +19,11 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, res, q):
+def _worker(rank, world, port, res, n_edits, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from ishapediting_b200.parallel import assign_edits, gather_results, gather_volume, slab_range
+    from ishapediting_b200.parallel import (assign_edits, decode_volume_sharded, gather_results, gather_volume,
+                                            slab_range)
     from tests.ref_ops import RefOps
 
     torch.set_num_threads(2)
@@ -34,24 +35,32 @@ def _worker(rank, world, port, res, q):
     lin = torch.linspace(-1, 1, res)
     slab = ops.decode_grid(planes_hwc, weights, lin, b, e, torch.zeros((e - b) * res * res)).view(e - b, res, res)
     vol = gather_volume(slab, res)
-    mine = assign_edits(5, rank, world)
+
+    def decode_slab(xb, xe, out):        # the kernel writes straight into its final offset of the full volume
+        ops.decode_grid(planes_hwc, weights, lin, xb, xe, out.view(-1))
+
+    vol2 = decode_volume_sharded(decode_slab, res, "cpu")
+    mine = assign_edits(n_edits, rank, world)
     local = torch.tensor([[float(k), float(k * k)] for k in mine])
-    allr = gather_results(local, 5)
+    allr = gather_results(local, n_edits)
     if rank == 0:
-        q.put((vol, allr))
+        q.put((vol, vol2, allr))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_slab_sharded_decode_and_edit_gather_world2():
-    res, world = 13, 2          # odd resolution: slabs of 7 and 6 rows
+@pytest.mark.parametrize("res,n_edits", [(13, 5), (12, 6)])
+def test_slab_sharded_decode_and_edit_gather_world2(res, n_edits):
+    """res=13: ragged slabs (7 + 6 rows, one broadcast per rank); res=12: equal slabs, ONE in-place
+    all_gather_into_tensor whose send buffer is this rank's slice of the receive buffer."""
+    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, res, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, res, n_edits, q)) for r in range(world)]
     for p in procs:
         p.start()
-    vol, allr = q.get()
+    vol, vol2, allr = q.get()
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
@@ -59,7 +68,8 @@ def test_slab_sharded_decode_and_edit_gather_world2():
     ref = O.decode_grid(w, planes, res).view(res, res, res)
     assert vol.shape == ref.shape
     assert float((vol - ref).abs().max()) < 1e-5          # disjoint slabs: no reduction-order issue
-    assert torch.equal(allr, torch.tensor([[float(k), float(k * k)] for k in range(5)]))
+    assert torch.equal(vol, vol2)
+    assert torch.equal(allr, torch.tensor([[float(k), float(k * k)] for k in range(n_edits)]))
 
 
 def test_slab_ranges_partition_the_grid():

@@ -143,3 +143,30 @@ def test_fractional_timesteps_are_embedded_as_floats():
         got = model(x.to(DEV), t.to(DEV))
     assert rel_l2(got, ref) < 1e-4
     assert rel_l2(trunc, ref) > 10 * rel_l2(got, ref)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_plans_of_different_batch_share_groupnorm_scratch(mode):
+    """The GroupNorm scratch buffer is shared by every plan of a model.  Its arrival counters must not move with
+    the batch size: with an N-dependent layout a batch-1 pass left partial sums where a batch-4 pass keeps the
+    counters of images 1..3, and those images then got wrong statistics (found by test_latent_inversion_nfd)."""
+    cfg = O.mid_cfg()
+    sd = O.synth_state_dict(cfg)
+    model, _ = build_model(cfg, sd, mode, DEV)
+    g = torch.Generator().manual_seed(3)
+    R = cfg["image_size"]
+    xs = torch.randn(4, cfg["in_out_channels"], R, R, generator=g).to(DEV)
+    ts = torch.tensor([246, 121, 116, 6], device=DEV)
+    fl = cfg["feat_layer"]
+    with torch.no_grad():
+        o4, f4 = model(xs, ts, feat_layer=fl)                       # sizes the shared scratch for N=4
+        singles = [model(xs[k:k + 1], ts[k:k + 1], feat_layer=fl) for k in range(4)]      # N=1 launches reuse it
+        o4b, f4b = model(xs, ts, feat_layer=fl)                      # N=4 again
+        o2, f2 = model(xs[:2], ts[:2], feat_layer=fl)
+    assert torch.equal(o4, o4b) and torch.equal(f4, f4b)
+    tol = 1e-5 if mode == "fp32" else 5e-3     # batch-N and batch-1 plans tile some layers differently
+    for k in range(4):
+        assert rel_l2(o4b[k:k + 1], singles[k][0]) < tol, k
+        assert rel_l2(f4b[k:k + 1], singles[k][1]) < tol, k
+    for k in range(2):
+        assert rel_l2(o2[k:k + 1], singles[k][0]) < tol, k
