@@ -569,7 +569,8 @@ def family_rooflines(st, ds, step_index, geo, feat_layer, use_graph, ms_full_ste
     peaks = _peaks()
     bpe = lambda t: 0 if t is None else t.numel() * t.element_size()  # noqa: E731
 
-    def ablate(patches):
+    def ablate(patches, record):
+        """ms per step with `patches` applied; record[:] is cut to what ONE step recorded."""
         saved = {k: getattr(ops, k) for k in patches}
         for k, v in patches.items():
             setattr(ops, k, v)
@@ -577,6 +578,7 @@ def family_rooflines(st, ds, step_index, geo, feat_layer, use_graph, ms_full_ste
             st2 = GuidedStepper(ds.model, ds.diffusion, geo, feat_layer, 0.2, "l2", 600.0, use_graph=use_graph)
             st2.img.copy_(ds.w)
             st2.step(step_index(0), ds.feature_guidance[0])
+            one_step = len(record)
             counted = True
             for k in range(1, 4):
                 st2.step(step_index(k), ds.feature_guidance[k % W_TIME])
@@ -588,6 +590,7 @@ def family_rooflines(st, ds, step_index, geo, feat_layer, use_graph, ms_full_ste
                 st2.step(step_index(k), ds.feature_guidance[k % W_TIME])
             e1.record()
             torch.cuda.synchronize()
+            del record[one_step:]
             return e0.elapsed_time(e1) / reps if counted else None
         finally:
             for k, v in saved.items():
@@ -597,12 +600,11 @@ def family_rooflines(st, ds, step_index, geo, feat_layer, use_graph, ms_full_ste
     rec = []
 
     def count_conv(a, w, bias, ksize, out, a2=None, residual=None, accumulate=False, tune=None, **kw):
-        if len(rec) < 10000:
-            rec.append(2.0 * a.shape[0] * a.shape[1] * a.shape[2] * w.shape[0] * w.shape[1])
+        rec.append(2.0 * a.shape[0] * a.shape[1] * a.shape[2] * w.shape[0] * w.shape[1])
 
-    ms_noconv = ablate({"conv": count_conv})
-    n_launch_rec = len(rec) // 24           # 1 eager + 3 + 20 steps were recorded
-    flops = sum(rec[:n_launch_rec])
+    ms_noconv = ablate({"conv": count_conv}, rec)
+    n_launch_rec = len(rec)
+    flops = sum(rec)
     t_ms = ms_full_step - ms_noconv
     tr = (traffic or {}).get("conv")
     conv = {"bound": "tensor", "kernel": "conv_tc_kernel + conv_tc2_kernel (tcgen05 implicit-GEMM conv / linear / dgrad)",
@@ -625,19 +627,17 @@ def family_rooflines(st, ds, step_index, geo, feat_layer, use_graph, ms_full_ste
     gbytes = []
 
     def count_gn_fwd(x1, x2, gamma, beta, film, film_off, silu, resample, stats, y, raw=None, xres=None, partials=None):
-        if len(gbytes) < 20000:
-            gbytes.append(bpe(x1) + bpe(x2) + bpe(y) + bpe(raw) + bpe(xres))
+        gbytes.append(bpe(x1) + bpe(x2) + bpe(y) + bpe(raw) + bpe(xres))
         return y
 
     def count_gn_bwd(x1, x2, gamma, beta, film, film_off, silu, resample, stats, dy, gres, gres_at_input,
                      gx1, acc1, gx1_lo, gx2, acc2, gx2_lo, partials=None):
-        if len(gbytes) < 20000:
-            gbytes.append(bpe(x1) + bpe(x2) + bpe(dy) + bpe(gres) + bpe(gx1) + bpe(gx1_lo) + bpe(gx2) + bpe(gx2_lo)
-                          + (bpe(gx1) if acc1 else 0) + (bpe(gx2) if acc2 else 0))
+        gbytes.append(bpe(x1) + bpe(x2) + bpe(dy) + bpe(gres) + bpe(gx1) + bpe(gx1_lo) + bpe(gx2) + bpe(gx2_lo)
+                      + (bpe(gx1) if acc1 else 0) + (bpe(gx2) if acc2 else 0))
 
-    ms_nogn = ablate({"gn_forward": count_gn_fwd, "gn_backward": count_gn_bwd})
-    n_gn = len(gbytes) // 24
-    gb = sum(gbytes[:n_gn])
+    ms_nogn = ablate({"gn_forward": count_gn_fwd, "gn_backward": count_gn_bwd}, gbytes)
+    n_gn = len(gbytes)
+    gb = sum(gbytes)
     t_gn = ms_full_step - ms_nogn
     trg = (traffic or {}).get("groupnorm")
     gn = {"bound": "hbm", "kernel": "gn_* (GroupNorm + FiLM + SiLU + resample + concat, forward and backward)",

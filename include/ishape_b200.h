@@ -290,6 +290,27 @@ int isb_drag_loss_grad(const isb_drag_desc* d, isb_stream_t stream);
 int isb_resize_feat_align(const float* feat, int S, int Cf, const int32_t* chan_map,
                           float* out, int Ca, isb_stream_t stream);
 
+/* ---- point tracking (OPT-IN EXTENSION; parity unpinned) ----------------- */
+/* BASELINE.json north_star names "point tracking ... nearest-feature search with a warp-level argmin"; the
+ * reference has no such function (handles and targets are fixed for a whole edit, drag_utils.py:305-321), so there
+ * is no reference interface this replaces.  For each of B handle points `center` [B,3] the (2r+1)^3 voxel lattice
+ * around it (offsets in drag_utils.make_offsets order, index = ((i+r)*side + (j+r))*side + (k+r), spacing `voxel`)
+ * is searched for the point whose aligned triplane feature (bilinear samples of the three planes, as in
+ * drag_utils.py:318-321,355-358) is nearest in L1 to f0 [B,3,Ca].  feat is the raw NHWC intermediate feature
+ * [1,S,S,Cf]; chan_map as for isb_drag_loss_grad.  table: scratch [B,3,(2r+1)^2] fp32 (the three separable
+ * distance tables, left filled for inspection).  Outputs: out_idx [B] int32 lattice index (ties -> lowest index),
+ * out_dist [B] fp32, out_pts [B,3] fp32 = center + voxel * offset. */
+typedef struct isb_track_desc {
+  const float* feat; int S; int Cf; int Ca;
+  const int32_t* chan_map;
+  const float* f0;
+  const float* center;
+  int B; int r; float voxel;
+  float* table;
+  int32_t* out_idx; float* out_dist; float* out_pts;
+} isb_track_desc;
+int isb_track_points(const isb_track_desc* d, isb_stream_t stream);
+
 /* ---- triplane decoder (axisnetworks.py:537-562, visualize.py:79-98) ---- */
 typedef struct isb_triplane_mlp {
   const float* fourier_B;      /* [32,64] */

@@ -101,6 +101,15 @@ class TriplaneMlp(C.Structure):
     ]
 
 
+class TrackDesc(C.Structure):
+    _fields_ = [
+        ("feat", c_void_p), ("S", c_int), ("Cf", c_int), ("Ca", c_int),
+        ("chan_map", c_void_p), ("f0", c_void_p), ("center", c_void_p),
+        ("B", c_int), ("r", c_int), ("voxel", C.c_float),
+        ("table", c_void_p), ("out_idx", c_void_p), ("out_dist", c_void_p), ("out_pts", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); also the list the symbol-export test checks against the header
 PROTOTYPES = {
     "isb_abi_version": (c_int, []),
@@ -130,6 +139,7 @@ PROTOTYPES = {
     "isb_drag_partial_len": (c_size_t, [c_int, c_int, c_int]),
     "isb_drag_loss_grad": (c_int, [C.POINTER(DragDesc), c_void_p]),
     "isb_resize_feat_align": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "isb_track_points": (c_int, [C.POINTER(TrackDesc), c_void_p]),
     "isb_triplane_decode_grid": (c_int, [c_void_p, c_int, C.POINTER(TriplaneMlp), c_void_p, c_int, c_int, c_int,
                                          c_void_p, c_void_p]),
     "isb_triplane_decode_points": (c_int, [c_void_p, c_int, C.POINTER(TriplaneMlp), c_void_p, C.c_int64,

@@ -107,6 +107,37 @@ def resize_feat_align(feature, cat_var=True):
 
 
 # ------------------------------------------------------------------------------------------------------
+# point tracking — OPT-IN EXTENSION, parity unpinned (the reference has no tracking function: SURVEY.md §0.3)
+# ------------------------------------------------------------------------------------------------------
+def handle_features(origin_feature, points):
+    """f0 [B,3,Ca]: the aligned triplane feature of each 3-D point (bilinear, align_corners=True, zeros — the sampling
+    of reference :355-358) taken from a cached origin feature (3,S,S,Ca channels-last, a feature_guidance entry)."""
+    pts = th.as_tensor(np.asarray(points), dtype=th.float32, device=origin_feature.device).reshape(-1, 3)
+    planes = origin_feature.permute(0, 3, 1, 2)                                   # (3, Ca, S, S) view
+    axes = ((0, 1), (1, 2), (0, 2))
+    grid = th.stack([pts[:, list(a)] for a in axes], dim=0).unsqueeze(2)          # (3, B, 1, 2): (u -> W, v -> H)
+    f = F.grid_sample(planes, grid, mode="bilinear", padding_mode="zeros", align_corners=True)   # (3, Ca, B, 1)
+    return f[..., 0].permute(2, 0, 1).contiguous()
+
+
+def track_points(feature_nhwc, f0, points, r, voxel_size, ops=None):
+    """Nearest-feature search with a warp-level argmin (isb_track_points): for every point, the lattice point within
+    r voxels whose aligned triplane feature in `feature_nhwc` ([1,S,S,Cf] raw intermediate feature, NHWC fp32) is
+    nearest in L1 to f0.  Returns (new_points [B,3], lattice index int32 [B], distance [B]).
+    This is an extension named by BASELINE.json's north_star; the reference keeps handles and targets fixed for a
+    whole edit (:305-321) and has nothing to compare against, so parity is unpinned."""
+    if ops is None:
+        from .ops import CudaOps
+        ops = CudaOps(feature_nhwc.device, "fp32")
+    chan_map, _, Ca = align_maps(feature_nhwc.shape[3])
+    center = th.as_tensor(np.asarray(points) if not th.is_tensor(points) else points, dtype=th.float32,
+                          device=ops.device).reshape(-1, 3).contiguous()
+    idx, dist, pts, _ = ops.track_points(feature_nhwc.contiguous(), chan_map.to(ops.device), f0.contiguous(), center,
+                                         r, voxel_size)
+    return pts, idx, dist
+
+
+# ------------------------------------------------------------------------------------------------------
 # geometry of one edit (host side, once per training() call)
 # ------------------------------------------------------------------------------------------------------
 class DragGeometry:
@@ -689,7 +720,11 @@ class DragStuff:
         return img
 
     # ---- the guided edit (reference :302-399) -----------------------------------------------------------
-    def training(self, sources=None, targets=None, scale=600, cof=0.2, noises=None):
+    def training(self, sources=None, targets=None, scale=600, cof=0.2, noises=None, track=False, track_radius=None):
+        """Reference :302-399.  `track=True` (opt-in extension, off by default; parity unpinned) additionally follows
+        the handles: after every step the point of the current feature nearest to each handle's ORIGINAL feature is
+        searched around its last tracked position (track_points); the positions are kept in self.tracked and the
+        L-inf distance to the targets, in voxels, in self.track_error — nothing of the guided update changes."""
         if self.args.num_samples > 1:
             raise NotImplementedError("We can handle only one shape at each time!")
         self.sources = th.tensor(np.asarray(sources), device=self.device, dtype=th.float32)
@@ -708,11 +743,20 @@ class DragStuff:
         stop_time = 0
         self.train_flag = True
         w_time = self.args.w_time
+        self.tracked, self.track_error = None, None
+        if track:
+            f0 = handle_features(self.feature_guidance[0], self.sources)
+            self.tracked = self.sources.clone()
+            inter = stepper.plan.block_out[self.args.feat_layer]
         for i in range(w_time - 1, -1, -1):
             if not self.train_flag:
                 stop_time = i + 1
                 break
             stepper.step(i, self.feature_guidance[w_time - 1 - i], None if noises is None else noises[w_time - 1 - i])
+            if track:
+                self.tracked, _, _ = track_points(inter.val, f0, self.tracked, track_radius or self.r1, self.voxel_size,
+                                                  ops=stepper.ops)
+                self.track_error = (self.tracked - self.targets).abs().amax(dim=1) / self.voxel_size
             yield 1 - i / (w_time - 1.) if w_time > 1 else 1.0
         self.mesh = self.get_mesh(img=stepper.img.clone(), t=stop_time)
 

@@ -181,11 +181,27 @@ class GaussianDiffusion:
         return {"mean": mean, "variance": var, "log_variance": th.log(var), "pred_xstart": x0,
                 "inter_feat": inter_feat, "model_output": eps}
 
+    def condition_mean(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
+        """Reference :364-377 (Sohl-Dickstein et al. conditioning): mean + variance * grad log p(y|x)."""
+        gradient = cond_fn(x, self._scale_timesteps(t), **(model_kwargs or {}))
+        return p_mean_var["mean"].float() + p_mean_var["variance"] * gradient.float()
+
+    def condition_score(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
+        """Reference :379-398 (Song et al. conditioning): eps <- eps - sqrt(1 - abar) * grad, then re-derive
+        pred_xstart and the posterior mean."""
+        alpha_bar = _extract_into_tensor(self.alphas_cumprod, t, x.shape)
+        eps = self._predict_eps_from_xstart(x, t, p_mean_var["pred_xstart"])
+        eps = eps - (1 - alpha_bar).sqrt() * cond_fn(x, self._scale_timesteps(t), **(model_kwargs or {}))
+        out = p_mean_var.copy()
+        out["pred_xstart"] = self._predict_xstart_from_eps(x, t, eps)
+        out["mean"], _, _ = self.q_posterior_mean_variance(out["pred_xstart"], x, t)
+        return out
+
     def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None):
-        if cond_fn is not None:
-            raise NotImplementedError("cond_fn is unused by the editor (drag_utils.py) and not implemented")
         out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
                                    model_kwargs=model_kwargs)
+        if cond_fn is not None:
+            out["mean"] = self.condition_mean(cond_fn, out, x, t, model_kwargs=model_kwargs)
         noise = th.randn_like(x)
         nonzero = (t != 0).float().view(-1, *([1] * (len(x.shape) - 1)))
         sample = out["mean"] + nonzero * th.exp(0.5 * out["log_variance"]) * noise
@@ -194,10 +210,10 @@ class GaussianDiffusion:
     def p_sample_guidance(self, model, x, t, noise=None, variance=None, variance_noise=None, clip_denoised=True,
                           denoised_fn=None, cond_fn=None, model_kwargs=None, **kwargs):
         """Reference :446-510 (same return dicts)."""
-        if cond_fn is not None:
-            raise NotImplementedError("cond_fn is unused by the editor (drag_utils.py) and not implemented")
         out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
                                    model_kwargs=model_kwargs, **kwargs)
+        if cond_fn is not None:
+            out["mean"] = self.condition_mean(cond_fn, out, x, t, model_kwargs=model_kwargs)
         nonzero = (t != 0).float().view(-1, *([1] * (len(x.shape) - 1)))
         if variance_noise is not None:
             return {"sample": out["mean"] + variance_noise, "inter_feat": out["inter_feat"], "variance": out["variance"]}
@@ -263,10 +279,10 @@ class GaussianDiffusion:
     def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
                     eta=0.0, **kwargs):
         """Reference :654-705 (shares the UNet + fused posterior; only the update differs)."""
-        if cond_fn is not None:
-            raise NotImplementedError("cond_fn is not implemented")
         out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
                                    model_kwargs=model_kwargs, **kwargs)
+        if cond_fn is not None:
+            out = self.condition_score(cond_fn, out, x, t, model_kwargs=model_kwargs)
         eps = self._predict_eps_from_xstart(x, t, out["pred_xstart"])
         alpha_bar = _extract_into_tensor(self.alphas_cumprod, t, x.shape)
         alpha_bar_prev = _extract_into_tensor(self.alphas_cumprod_prev, t, x.shape)

@@ -60,6 +60,14 @@ class SpacedDiffusion(GaussianDiffusion):
     def p_mean_variance(self, model, *args, **kwargs):
         return super().p_mean_variance(self._wrap_model(model), *args, **kwargs)
 
+    def condition_mean(self, cond_fn, *args, **kwargs):
+        """Reference respace.py:97-98: cond_fn sees ORIGINAL timesteps, like the model."""
+        return super().condition_mean(self._wrap_model(cond_fn), *args, **kwargs)
+
+    def condition_score(self, cond_fn, *args, **kwargs):
+        """Reference respace.py:100-101."""
+        return super().condition_score(self._wrap_model(cond_fn), *args, **kwargs)
+
     def _wrap_model(self, model):
         if isinstance(model, _WrappedModel):
             return model

@@ -401,6 +401,24 @@ class CudaOps:
         d.dyn_scalars = _p(_chk(dyn, torch.float32)) if dyn is not None else None
         _lib.check(self.lib.isb_drag_loss_grad(C.byref(d), _stream()), "isb_drag_loss_grad")
 
+    def track_points(self, feat, chan_map, f0, center, r, voxel, table=None):
+        """Opt-in nearest-feature tracking (isb_track_points): feat [1,S,S,Cf] fp32 NHWC, f0 [B,3,Ca], center [B,3].
+        Returns (idx int32 [B], dist [B], pts [B,3], table [B,3,(2r+1)^2])."""
+        _chk(feat, torch.float32); _chk(chan_map, torch.int32); _chk(f0, torch.float32); _chk(center, torch.float32)
+        B, side = center.shape[0], 2 * r + 1
+        assert f0.shape[0] == B and f0.shape[1] == 3 and chan_map.numel() == 3 * f0.shape[2]
+        if table is None:
+            table = self.empty((B, 3, side * side))
+        idx = torch.empty((B,), dtype=torch.int32, device=self.device)
+        dist, pts = self.empty((B,)), self.empty((B, 3))
+        d = _lib.TrackDesc()
+        d.feat, d.S, d.Cf, d.Ca = _p(feat), feat.shape[1], feat.shape[3], f0.shape[2]
+        d.chan_map, d.f0, d.center = _p(chan_map), _p(f0), _p(center)
+        d.B, d.r, d.voxel = B, int(r), float(voxel)
+        d.table, d.out_idx, d.out_dist, d.out_pts = _p(_chk(table, torch.float32)), _p(idx), _p(dist), _p(pts)
+        _lib.check(self.lib.isb_track_points(C.byref(d), _stream()), "isb_track_points")
+        return idx, dist, pts, table
+
     # ---- triplane decoder ---------------------------------------------------------------------
     @staticmethod
     def _mlp(weights):

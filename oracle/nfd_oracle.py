@@ -276,6 +276,8 @@ class Schedule:
         self.posterior_log_variance_clipped = np.log(np.append(self.posterior_variance[1], self.posterior_variance[1:]))
         self.posterior_mean_coef1 = betas * np.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
         self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - self.alphas_cumprod)
+        self.alphas_cumprod_next = np.append(self.alphas_cumprod[1:], 0.0)                 # :151
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - self.alphas_cumprod)           # :156
 
 
 def _f(a, i):
@@ -304,6 +306,62 @@ def p_sample_guidance(sd, cfg, sched, x, i, noise, feat_layer=8, clip_denoised=T
     nonzero = 0.0 if i == 0 else 1.0
     sample = mean + nonzero * torch.sqrt(var) * noise
     return dict(sample=sample, pred_xstart=x0, inter_feat=inter, model_output=eps, noise=noise, variance=var, mean=mean)
+
+
+# ------------------------------------------------------------------------------------------------
+# DDIM variants and cond_fn conditioning (gaussian_diffusion.py:364-398, 400-444, 654-761)
+# ------------------------------------------------------------------------------------------------
+def _eps_from_xstart(sched, x, i, x0):
+    """_predict_eps_from_xstart (:351-355)."""
+    return (_f(sched.sqrt_recip_alphas_cumprod, i) * x - x0) / _f(sched.sqrt_recipm1_alphas_cumprod, i)
+
+
+def p_sample_cond(sd, cfg, sched, x, i, noise, cond_fn):
+    """p_sample with cond_fn (:400-444): condition_mean (:364-377) shifts the posterior mean by variance * grad;
+    the sample uses exp(0.5 * log_variance) (:443), unlike p_sample_guidance's sqrt(variance)."""
+    o = p_sample_guidance(sd, cfg, sched, x, i, noise, feat_layer=-1)
+    t = torch.full((x.shape[0],), sched.timestep_map[i], dtype=torch.int64)     # respace.py:97-101: original t
+    mean = o["mean"].float() + o["variance"] * cond_fn(x, t).float()
+    nonzero = 0.0 if i == 0 else 1.0
+    return dict(sample=mean + nonzero * torch.exp(0.5 * torch.log(o["variance"])) * noise, pred_xstart=o["pred_xstart"],
+                mean=mean)
+
+
+def ddim_sample(sd, cfg, sched, x, i, noise, eta=0.0, cond_fn=None, feat_layer=-1):
+    """ddim_sample (:654-705) with optional condition_score (:379-398)."""
+    o = p_sample_guidance(sd, cfg, sched, x, i, noise, feat_layer=feat_layer)
+    x0 = o["pred_xstart"]
+    abar, abar_prev = _f(sched.alphas_cumprod, i), _f(sched.alphas_cumprod_prev, i)
+    if cond_fn is not None:
+        t = torch.full((x.shape[0],), sched.timestep_map[i], dtype=torch.int64)     # respace.py:97-101: original t
+        eps = _eps_from_xstart(sched, x, i, x0) - (1 - abar).sqrt() * cond_fn(x, t)
+        x0 = _f(sched.sqrt_recip_alphas_cumprod, i) * x - _f(sched.sqrt_recipm1_alphas_cumprod, i) * eps
+    eps = _eps_from_xstart(sched, x, i, x0)
+    sigma = eta * torch.sqrt((1 - abar_prev) / (1 - abar)) * torch.sqrt(1 - abar / abar_prev)
+    mean_pred = x0 * torch.sqrt(abar_prev) + torch.sqrt(1 - abar_prev - sigma ** 2) * eps
+    nonzero = 0.0 if i == 0 else 1.0
+    return dict(sample=mean_pred + nonzero * sigma * noise, pred_xstart=x0, inter_feat=o["inter_feat"],
+                model_output=o["model_output"])
+
+
+def ddim_reverse_sample(sd, cfg, sched, x, i):
+    """ddim_reverse_sample (:718-761): x_{t+1} along the deterministic DDIM ODE."""
+    o = p_sample_guidance(sd, cfg, sched, x, i, torch.zeros_like(x), feat_layer=-1)
+    eps = _eps_from_xstart(sched, x, i, o["pred_xstart"])
+    abar_next = _f(sched.alphas_cumprod_next, i)
+    return dict(sample=o["pred_xstart"] * torch.sqrt(abar_next) + torch.sqrt(1 - abar_next) * eps,
+                pred_xstart=o["pred_xstart"])
+
+
+def ddim_guidance_sample(sched, eps, grads, xt, i, clip_denoised=True):
+    """ddim_guidance_sample (:707-716)."""
+    eps = eps - _f(sched.sqrt_one_minus_alphas_cumprod, i) * grads
+    x0 = _f(sched.sqrt_recip_alphas_cumprod, i) * xt - _f(sched.sqrt_recipm1_alphas_cumprod, i) * eps
+    if clip_denoised:
+        x0 = x0.clamp(-1, 1)
+    eps = _eps_from_xstart(sched, xt, i, x0)
+    abar_prev = _f(sched.alphas_cumprod_prev, i)
+    return x0 * torch.sqrt(abar_prev) + torch.sqrt(1 - abar_prev) * eps
 
 
 # ------------------------------------------------------------------------------------------------

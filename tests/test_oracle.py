@@ -128,3 +128,38 @@ def test_oracle_matches_live_reference_unet_and_schedule():
             for k in ("sample", "pred_xstart", "model_output", "variance", "mean", "inter_feat"):
                 assert torch.equal(ref[k], mine[k]), (i, k)
         assert torch.equal(ns.drag_utils.resize_feat_align(ref["inter_feat"]), O.resize_feat_align(mine["inter_feat"]))
+
+
+@pytest.mark.skipif(not R.available(), reason="needs /root/reference or the oracle/_ref snapshot")
+def test_oracle_ddim_and_cond_fn_match_live_reference(monkeypatch):
+    """DDIM variants (gaussian_diffusion.py:654-761) and cond_fn conditioning (:364-398, respace.py:97-101) of the
+    oracle against the reference's own SpacedDiffusion + UNet; th.randn_like is pinned so that eta > 0 is comparable."""
+    cfg = O.small_cfg()
+    ns, model, diffusion = R.reference_model_and_diffusion(cfg)
+    sd = O.synth_state_dict(cfg)
+    model.load_state_dict(sd, strict=True)
+    x, x2, noise = _inputs(cfg)
+    sched = O.Schedule(cfg["diffusion_steps"], cfg["timestep_respacing"])
+    monkeypatch.setattr(torch, "randn_like", lambda t, **kw: noise.to(t.device))
+    seen = []
+
+    def cond_fn(xx, t, **kw):
+        seen.append(int(t[0]))
+        return 0.05 * torch.sin(3.0 * xx) * (1.0 + 0.001 * t.float().view(-1, 1, 1, 1))
+
+    with torch.no_grad():
+        for i in (150, 49, 0):
+            t = torch.tensor([i])
+            for eta, cf in ((0.0, None), (0.5, None), (0.0, cond_fn)):
+                ref = diffusion.ddim_sample(model, x, t, eta=eta, cond_fn=cf, model_kwargs={})
+                mine = O.ddim_sample(sd, cfg, sched, x, i, noise, eta=eta, cond_fn=cf)
+                assert rel_l2(mine["sample"], ref["sample"]) < 1e-6, (i, eta)
+                assert rel_l2(mine["pred_xstart"], ref["pred_xstart"]) < 1e-6, (i, eta)
+            ref = diffusion.ddim_reverse_sample(model, x, t)
+            assert rel_l2(O.ddim_reverse_sample(sd, cfg, sched, x, i)["sample"], ref["sample"]) < 1e-6
+            ref = diffusion.ddim_guidance_sample(x2.clone(), 0.1 * noise, x, t)
+            assert rel_l2(O.ddim_guidance_sample(sched, x2.clone(), 0.1 * noise, x, i), ref) < 1e-6
+            ref = diffusion.p_sample(model, x, t, cond_fn=cond_fn, model_kwargs={})
+            mine = O.p_sample_cond(sd, cfg, sched, x, i, noise, cond_fn)
+            assert rel_l2(mine["sample"], ref["sample"]) < 1e-6, i
+    assert set(seen) == {sched.timestep_map[i] for i in (150, 49, 0)}       # cond_fn sees ORIGINAL timesteps

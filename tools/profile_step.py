@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--mode", default="bf16")
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--time-ops", action="store_true", help="CUDA-event time per op family (eager)")
+    ap.add_argument("--algbytes", default=None, help="write per-family algorithmic bytes of one step to this JSON")
+    ap.add_argument("--decode", type=int, default=0, help="also profile one dense decode at this resolution")
     args = ap.parse_args()
     dev = "cuda:0"
     cfg = O.NFD_CFG
@@ -80,9 +82,55 @@ def main():
             fl = 2.0 * int(hw[0]) * int(hw[1]) * cout * K * n
             print(f"  {k:44s} x{n:3d} {t:8.3f} ms {fl / t / 1e9:8.1f}")
         return
+    if args.algbytes:
+        import json
+        ops = st.ops
+        bpe = lambda t: 0 if t is None else t.numel() * t.element_size()  # noqa: E731
+        acc = {"conv": {"launches": 0, "bytes": 0}, "groupnorm": {"launches": 0, "bytes": 0}}
+        conv0, gnf0, gnb0 = ops.conv, ops.gn_forward, ops.gn_backward
+
+        def conv(a, w, bias, ksize, out, a2=None, residual=None, **kw):
+            wd = w.data if hasattr(w, "data") and not torch.is_tensor(w) else w
+            acc["conv"]["launches"] += 1
+            acc["conv"]["bytes"] += bpe(a) + bpe(a2) + bpe(wd) + bpe(out) + bpe(residual) + bpe(bias)
+            return conv0(a, w, bias, ksize, out, a2=a2, residual=residual, **kw)
+
+        def gnf(x1, x2, *a, **kw):
+            y = a[7]
+            acc["groupnorm"]["launches"] += 1
+            acc["groupnorm"]["bytes"] += bpe(x1) + bpe(x2) + bpe(y) + bpe(kw.get("raw")) + bpe(kw.get("xres"))
+            return gnf0(x1, x2, *a, **kw)
+
+        def gnb(x1, x2, gamma, beta, film, film_off, silu, resample, stats, dy, gres, gres_at_input, gx1, acc1, gx1_lo,
+                gx2, acc2, gx2_lo, **kw):
+            acc["groupnorm"]["launches"] += 1
+            acc["groupnorm"]["bytes"] += (bpe(x1) + bpe(x2) + bpe(dy) + bpe(gres) + bpe(gx1) + bpe(gx1_lo) + bpe(gx2)
+                                          + bpe(gx2_lo) + (bpe(gx1) if acc1 else 0) + (bpe(gx2) if acc2 else 0))
+            return gnb0(x1, x2, gamma, beta, film, film_off, silu, resample, stats, dy, gres, gres_at_input, gx1, acc1,
+                        gx1_lo, gx2, acc2, gx2_lo, **kw)
+
+        ops.conv, ops.gn_forward, ops.gn_backward = conv, gnf, gnb
+        st.step(48, origin)
+        torch.cuda.synchronize()
+        ops.conv, ops.gn_forward, ops.gn_backward = conv0, gnf0, gnb0
+        if args.decode:
+            acc["decode"] = {"launches": 1, "bytes": 4 * args.decode ** 3 + 3 * 32 * 128 * 128 * 4}
+        with open(args.algbytes, "w") as f:
+            json.dump(acc, f)
+    dec = None
+    if args.decode:
+        from tests.helpers import build_decoder
+        from ishapediting_b200.triplane_decoder.visualize import query_volume
+        dec, _, planes = build_decoder(128, dev)
+        for p in range(3):
+            dec.embeddings[p] = planes[[p]].to(dev)
+        query_volume(dec, 0, res=args.decode)
+        torch.cuda.synchronize()
     torch.cuda.profiler.start()
     for s in range(args.steps):
         st.step(48 - s, origin)
+    if dec is not None:
+        query_volume(dec, 0, res=args.decode)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     print("profiled", args.steps, "step(s)")
