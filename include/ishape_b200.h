@@ -317,6 +317,11 @@ typedef struct isb_triplane_mlp {
   const float* w1; const float* b1;  /* [128,128],[128] */
   const float* w2; const float* b2;  /* [128,128],[128] */
   const float* w3; const float* b3;  /* [1,128],[1] */
+  /* Upper bound of the layer-1 pre-activations, max_r(sum_k |w1[r,k]| + |b1[r]|) (its inputs are sines / cosines),
+   * computed once by the host.  > 0 and fp16-safe (<= 30000): the two 128x128 layers run on tcgen05 as split-fp16
+   * (hi + lo) products with fp32 TMEM accumulation (decode_tc.cu, fp32-grade results).  0 = unknown: the 3xTF32
+   * mma.sync kernel (decode.cu) is used.  Both are GPU paths with the same results to ~1e-6. */
+  float h1_bound;
 } isb_triplane_mlp;
 /* planes_hwc: [3,R,R,32] fp32 channels-last (isb_nchw_to_nhwc of the reference's
  * three (1,32,R,R) embeddings).  Dense grid query of lin^3 where lin[res] is the

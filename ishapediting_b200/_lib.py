@@ -98,6 +98,7 @@ class TriplaneMlp(C.Structure):
         ("w1", c_void_p), ("b1", c_void_p),
         ("w2", c_void_p), ("b2", c_void_p),
         ("w3", c_void_p), ("b3", c_void_p),
+        ("h1_bound", C.c_float),
     ]
 
 

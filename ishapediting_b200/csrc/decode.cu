@@ -401,6 +401,12 @@ static int decode_bwd_launch(const DecodeBwdArgs& a, cudaStream_t st) {
   return ISB_OK;
 }
 
+// decode_tc.cu: the same forward with the two 128x128 layers on tcgen05 (split-fp16, fp32-grade)
+int decode_tc_init();
+bool decode_tc_usable(float h1_bound);
+int decode_tc_launch(const float* planes, int R, const isb_triplane_mlp* w, const float* lin, int res, long long idx0,
+                     const float* coords, long long npts, float* out, bool grid_mode, cudaStream_t st);
+
 static int decode_launch(const DecodeArgs& a, bool grid_mode, cudaStream_t st) {
   const long long ntiles = (a.npts + DC_TP - 1) / DC_TP;
   long long blocks = ntiles < num_sms() ? ntiles : num_sms();
@@ -416,7 +422,7 @@ int decode_init() {
   ISB_CUDA(cudaFuncSetAttribute(triplane_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(DecodeSmem)));
   ISB_CUDA(cudaFuncSetAttribute(triplane_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(DecodeSmem)));
   ISB_CUDA(cudaFuncSetAttribute(triplane_decode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(DecodeBwdSmem)));
-  return ISB_OK;
+  return decode_tc_init();
 }
 
 }  // namespace isb
@@ -427,6 +433,9 @@ int isb_triplane_decode_grid(const float* planes_hwc, int R, const isb_triplane_
                              int x_begin, int x_end, float* out, isb_stream_t stream) {
   ISB_CHECK_ARG(planes_hwc && w && lin && out, "isb_triplane_decode_grid: null pointer");
   ISB_CHECK_ARG(R > 1 && res > 1 && x_begin >= 0 && x_end <= res && x_begin <= x_end, "isb_triplane_decode_grid: bad range");
+  if (isb::decode_tc_usable(w->h1_bound))
+    return isb::decode_tc_launch(planes_hwc, R, w, lin, res, static_cast<long long>(x_begin) * res * res, nullptr,
+                                 static_cast<long long>(x_end - x_begin) * res * res, out, true, isb::as_stream(stream));
   isb::DecodeArgs a{planes_hwc, R, w->fourier_B, w->w1, w->b1, w->w2, w->b2, w->w3, w->b3,
                     lin, res, static_cast<long long>(x_begin) * res * res, nullptr,
                     static_cast<long long>(x_end - x_begin) * res * res, out};
@@ -436,6 +445,9 @@ int isb_triplane_decode_grid(const float* planes_hwc, int R, const isb_triplane_
 int isb_triplane_decode_points(const float* planes_hwc, int R, const isb_triplane_mlp* w, const float* coords,
                                int64_t npts, float* out, isb_stream_t stream) {
   ISB_CHECK_ARG(planes_hwc && w && coords && out && npts >= 0, "isb_triplane_decode_points: null pointer");
+  if (isb::decode_tc_usable(w->h1_bound))
+    return isb::decode_tc_launch(planes_hwc, R, w, nullptr, 0, 0, coords, static_cast<long long>(npts), out, false,
+                                 isb::as_stream(stream));
   isb::DecodeArgs a{planes_hwc, R, w->fourier_B, w->w1, w->b1, w->w2, w->b2, w->w3, w->b3,
                     nullptr, 0, 0, coords, static_cast<long long>(npts), out};
   return isb::decode_launch(a, false, isb::as_stream(stream));

@@ -66,6 +66,7 @@ class CudaOps:
         # (GuidedStepper / ReconStepper / the no-grad step graph share this ops object per model), and their arrival
         # counters must stay 0 between launches, so they are never returned to the caching allocator.
         self._retired = []
+        self._mlp_bounds = {}
 
     # ---- memory -----------------------------------------------------------
     def empty(self, shape, dtype=torch.float32):
@@ -420,10 +421,23 @@ class CudaOps:
         return idx, dist, pts, table
 
     # ---- triplane decoder ---------------------------------------------------------------------
-    @staticmethod
-    def _mlp(weights):
+    def _mlp(self, weights):
         m = _lib.TriplaneMlp()
         m.fourier_B, m.w1, m.b1, m.w2, m.b2, m.w3, m.b3 = (_p(_chk(w, torch.float32)) for w in weights)
+        # bound of the hidden pre-activations (layer-1 inputs are sin / cos): selects the split-fp16 tcgen05 decoder
+        # when it is fp16-safe.  One device reduction + read-back per weight version, never inside a graph capture.
+        w1, b1 = weights[1], weights[2]
+        key = (w1.data_ptr(), w1._version, b1.data_ptr(), b1._version)
+        bound = self._mlp_bounds.get(key)
+        if bound is None:
+            if torch.cuda.is_current_stream_capturing() or os.environ.get("ISB_DECODE_TC", "1") == "0":
+                bound = 0.0
+            else:
+                bound = float((w1.abs().sum(dim=1) + b1.abs()).max().item())
+                if len(self._mlp_bounds) > 64:
+                    self._mlp_bounds.clear()
+                self._mlp_bounds[key] = bound
+        m.h1_bound = bound
         return m
 
     def decode_grid(self, planes_hwc, weights, lin, x_begin, x_end, out):
