@@ -15,15 +15,17 @@
 // The host passes that bound (isb_triplane_mlp.h1_bound); this kernel is used only when it is fp16-safe, otherwise the
 // 3xTF32 mma.sync kernel of decode.cu runs (same results, slower).
 //
-// One persistent CTA per SM (219 KB of shared memory: both layers' weights as hi / lo' fp16 K-major 128B-swizzled
-// UMMA tiles = 128 KB, one A operand pair = 64 KB, staging).  288 threads: warps 0-7 compute (sampling, Fourier
-// features, operand splitting, epilogues), warp 8 issues the MMAs.  Per 128-point tile:
-//   P1  bilinear plane samples -> f[32]            (2 threads per point, 16 channels each)
-//   P2  u = f @ B, [sin | cos](2 pi u) -> A_hi / A_lo in UMMA layout              -> mbarrier a_ready
+// One persistent CTA per SM (220 KB of shared memory: both layers' weights as hi / lo' fp16 K-major 128B-swizzled
+// UMMA tiles = 128 KB, one A operand pair = 64 KB, staging).  544 threads: warps 0-15 compute (sampling, Fourier
+// features, operand splitting, epilogues; 4 warps per TMEM lane quarter), warp 16 issues the MMAs.  Per 128-point
+// tile i, software-pipelined so that the tensor cores never wait for the sampling of their own tile:
+//   S0  [sin | cos](2 pi u_i) -> A_hi / A_lo in UMMA layout                        -> mbarrier a_ready
 //   M1  D1 = A_hi W1hi^T + A_lo W1hi^T,  D1' = A_hi W1lo'^T   (24 MMAs 128x128x16) -> tcgen05.commit d_ready
-//   P3  h1 = relu(D1 + 2^-11 D1' + b1) -> split -> A_hi / A_lo (layer-2 operand)  -> a_ready
-//   M2  D2, D2' likewise with W2                                                 -> d_ready
-//   P4  logit = w3 . relu(D2 + 2^-11 D2' + b2) + b3  (fp32 registers)            -> global
+//   S1  (under M1) bilinear plane samples of tile i+1 -> F[32][128]
+//   S2  h1 = relu(D1 + 2^-11 D1' + b1) -> split -> A_hi / A_lo (layer-2 operand)   -> a_ready
+//   M2  D2, D2' likewise with W2                                                  -> d_ready
+//   S3  (under M2) u_{i+1} = F @ B  (fp32 FFMA, 4x4 register tiles; stays in registers)
+//   S4  logit = w3 . relu(D2 + 2^-11 D2' + b2) + b3  (fp32 registers)             -> global
 #include "common.cuh"
 
 namespace isb {
@@ -31,18 +33,19 @@ namespace dtc {
 
 constexpr int TP = 128;                 // points per tile = UMMA M
 constexpr int H = 128, F = 32, MF = 64; // hidden width, plane features, Fourier frequencies
-constexpr int COMPUTE_THREADS = 256;
+constexpr int COMPUTE_THREADS = 512;    // 16 compute warps: 4 per TMEM lane quarter, 4 per scheduler (latency hiding)
 constexpr int THREADS = COMPUTE_THREADS + 32;
 constexpr int ATOM = TP * 128;          // one K-atom: 128 rows x 64 fp16 = 16 KiB
 constexpr int OPER = 2 * ATOM;          // one 128x128 fp16 operand = 32 KiB
+constexpr int FLD = TP + 4;             // row pitch of the transposed feature staging F[c][pt]
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int OFF_W1H = 0, OFF_W1L = OPER, OFF_W2H = 2 * OPER, OFF_W2L = 3 * OPER;
 constexpr int OFF_AH = 4 * OPER, OFF_AL = 5 * OPER;
-constexpr int OFF_F = 6 * OPER;                      // float F[128][33]
-constexpr int OFF_BM = OFF_F + TP * 33 * 4;          // float Bm[32][64]
+constexpr int OFF_F = 6 * OPER;                      // float F[32][132]
+constexpr int OFF_BM = OFF_F + F * FLD * 4;          // float Bm[32][64]
 constexpr int OFF_VEC = OFF_BM + F * MF * 4;         // float b1[128], b2[128], w3[128]
-constexpr int OFF_X = OFF_VEC + 3 * H * 4;           // float xch[128]
-constexpr int SMEM_BYTES = OFF_X + TP * 4 + 1024;    // + alignment slack
+constexpr int OFF_X = OFF_VEC + 3 * H * 4;           // float xch[3][128]
+constexpr int SMEM_BYTES = OFF_X + 3 * TP * 4 + 1024;  // + alignment slack
 
 struct Args {
   const float* planes; int R;
@@ -52,6 +55,7 @@ struct Args {
   const float* coords;
   long long npts;
   float* out;
+  int fast_rows;   // grid mode, res % 128 == 0, <= 31 plane rows per 32 consecutive z: cooperative row sampling
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -121,6 +125,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// sin and cos of x to ~1 ulp (measured 7e-8 absolute against float64 for |x| <= 4e4, tools note in DESIGN.md):
+// three-term Cody-Waite reduction by pi/2 and the two degree-7/8 kernels on |r| <= pi/4, i.e. the fast path of
+// sincosf() without its slow-path branch, denormal handling and local-memory frame; arguments beyond the reduction's
+// range (never reached by 2*pi*f@B in practice) take the library call.
+__device__ __forceinline__ void sincos_cw(float x, float& sn, float& cs) {
+  if (fabsf(x) > 40000.0f) {
+    sincosf(x, &sn, &cs);
+    return;
+  }
+  const float k = rintf(x * 0.636619772f);
+  const int q = static_cast<int>(k);
+  float r = fmaf(k, -1.57079601e+00f, x);
+  r = fmaf(k, -3.13916473e-07f, r);
+  r = fmaf(k, -5.39030253e-15f, r);
+  const float r2 = r * r;
+  float p = 2.86567956e-6f;
+  p = fmaf(p, r2, -1.98559923e-4f);
+  p = fmaf(p, r2, 8.33338592e-3f);
+  p = fmaf(p, r2, -1.66666672e-1f);
+  const float s = fmaf(p, r * r2, r);
+  float c = 2.44677067e-5f;
+  c = fmaf(c, r2, -1.38877297e-3f);
+  c = fmaf(c, r2, 4.16666567e-2f);
+  c = fmaf(c, r2, -0.5f);
+  c = fmaf(c, r2, 1.0f);
+  const float a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+  sn = (q & 2) ? -a : a;
+  cs = ((q + 1) & 2) ? -b : b;
+}
+
 // byte offset of the 16-byte chunk holding elements [k8*8, k8*8+8) of row r inside a 128x128 fp16 operand
 __device__ __forceinline__ uint32_t chunk_off(int r, int k8) {
   return static_cast<uint32_t>((k8 >> 3) * ATOM + (r >> 3) * 1024 + (r & 7) * 128 + (((k8 & 7) ^ (r & 7)) << 4));
@@ -142,7 +176,7 @@ __device__ __forceinline__ void store_chunk(uint32_t a_hi, uint32_t a_lo, int r,
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
 }
 
-__device__ __forceinline__ void sample_plane16(const float* __restrict__ plane, int R, float gx, float gy, int c0, float* acc) {
+__device__ __forceinline__ void sample_plane8(const float* __restrict__ plane, int R, float gx, float gy, int c0, float* acc) {
   const float ix = ((gx + 1.0f) / 2.0f) * static_cast<float>(R - 1);       // grid_sample, align_corners=True
   const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(R - 1);
   const float fx0 = floorf(ix), fy0 = floorf(iy);
@@ -156,13 +190,110 @@ __device__ __forceinline__ void sample_plane16(const float* __restrict__ plane, 
       if (x < 0 || x >= R || y < 0 || y >= R) continue;                     // zeros padding
       const float w = (dx ? fx : 1.0f - fx) * (dy ? fy : 1.0f - fy);
       const float4* p = reinterpret_cast<const float4*>(plane + (static_cast<size_t>(y) * R + x) * F + c0);
+      const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
+      acc[0] = fmaf(w, v0.x, acc[0]); acc[1] = fmaf(w, v0.y, acc[1]); acc[2] = fmaf(w, v0.z, acc[2]); acc[3] = fmaf(w, v0.w, acc[3]);
+      acc[4] = fmaf(w, v1.x, acc[4]); acc[5] = fmaf(w, v1.y, acc[5]); acc[6] = fmaf(w, v1.z, acc[6]); acc[7] = fmaf(w, v1.w, acc[7]);
+    }
+}
+
+// plane samples of point (tile, pt), channels c0..c0+7 (zeros for points past the end)
+template <bool GRID>
+__device__ __forceinline__ void sample_point(const Args& a, long long tile, int pt, int c0, float* f) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 v = __ldg(p + q);
-        acc[4 * q] = fmaf(w, v.x, acc[4 * q]); acc[4 * q + 1] = fmaf(w, v.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(w, v.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, v.w, acc[4 * q + 3]);
+  for (int j = 0; j < 8; ++j) f[j] = 0.f;
+  const long long i = tile * TP + pt;
+  if (i >= a.npts) return;
+  float cx, cy, cz;
+  if (GRID) {
+    const long long gi = a.idx0 + i;
+    const int z = static_cast<int>(gi % a.res);
+    const long long t = gi / a.res;
+    const int y = static_cast<int>(t % a.res);
+    const int x = static_cast<int>(t / a.res);
+    cx = __ldg(a.lin + x); cy = __ldg(a.lin + y); cz = __ldg(a.lin + z);
+  } else {
+    cx = __ldg(a.coords + i * 3); cy = __ldg(a.coords + i * 3 + 1); cz = __ldg(a.coords + i * 3 + 2);
+  }
+  const size_t plane_sz = static_cast<size_t>(a.R) * a.R * F;
+  sample_plane8(a.planes, a.R, cx, cy, c0, f);                 // xy plane: x->W, y->H
+  sample_plane8(a.planes + plane_sz, a.R, cy, cz, c0, f);      // yz plane
+  sample_plane8(a.planes + 2 * plane_sz, a.R, cx, cz, c0, f);  // xz plane
+}
+
+// Grid mode with res % 128 == 0: the 32 points of a warp are consecutive in z at one (x, y).  Then
+//     f(z) = xy(x, y) + (1 - fy(z)) G[y0(z)] + fy(z) G[y0(z) + 1],    G[row] = lerp_x(yz plane)[row] + lerp_x(xz plane)[row]
+// (bilinear interpolation separates, and both z-planes are sampled at the same row coordinate).  Lane j loads the
+// combined row y0(lane 0) + j ONCE (4 pixels) and every lane fetches its two rows with warp shuffles: 16 loads per lane
+// instead of 24, and 6x fewer distinct cache lines per tile than per-point sampling (the L1 is only ~28 KB next to 219 KB
+// of shared memory: per-point sampling was 40 % of the kernel's stall samples, profiles/r02_decode_tc.md).
+__device__ __forceinline__ void sample_rows_fast(const Args& a, long long tile, int wq, int lane, int c0, float* f) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = 0.f;
+  const long long gi0 = a.idx0 + tile * TP + wq * 32;
+  const int z0 = static_cast<int>(gi0 % a.res);
+  const long long t = gi0 / a.res;
+  const int y = static_cast<int>(t % a.res);
+  const int x = static_cast<int>(t / a.res);
+  const float cx = __ldg(a.lin + x), cy = __ldg(a.lin + y), cz = __ldg(a.lin + z0 + lane);
+  const int R = a.R;
+  const size_t plane_sz = static_cast<size_t>(R) * R * F;
+  sample_plane8(a.planes, R, cx, cy, c0, f);                    // xy plane: one broadcast sample for the warp
+  const float iy = ((cz + 1.0f) / 2.0f) * static_cast<float>(R - 1);
+  const float fy0 = floorf(iy);
+  const int y0 = static_cast<int>(fy0);
+  const float fy = iy - fy0;
+  const int rbase = __shfl_sync(0xffffffffu, y0, 0);
+  const int rlast = __shfl_sync(0xffffffffu, y0, 31) + 1;         // last row any lane of this warp reads
+  const int row = rbase + lane;
+  float g[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  if (row >= 0 && row < R && row <= rlast) {
+#pragma unroll
+    for (int pl = 1; pl <= 2; ++pl) {
+      const float gx = pl == 1 ? cy : cx;                         // yz plane: y -> W;  xz plane: x -> W
+      const float ix = ((gx + 1.0f) / 2.0f) * static_cast<float>(R - 1);
+      const float fx0 = floorf(ix);
+      const int x0 = static_cast<int>(fx0);
+      const float fx = ix - fx0;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int xx = x0 + dx;
+        if (xx < 0 || xx >= R) continue;
+        const float w = dx ? fx : 1.0f - fx;
+        const float4* p = reinterpret_cast<const float4*>(a.planes + pl * plane_sz + (static_cast<size_t>(row) * R + xx) * F + c0);
+        const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
+        g[0] = fmaf(w, v0.x, g[0]); g[1] = fmaf(w, v0.y, g[1]); g[2] = fmaf(w, v0.z, g[2]); g[3] = fmaf(w, v0.w, g[3]);
+        g[4] = fmaf(w, v1.x, g[4]); g[5] = fmaf(w, v1.y, g[5]); g[6] = fmaf(w, v1.z, g[6]); g[7] = fmaf(w, v1.w, g[7]);
       }
     }
+  }
+  const int j0 = y0 - rbase;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float v0 = __shfl_sync(0xffffffffu, g[j], j0);
+    const float v1 = __shfl_sync(0xffffffffu, g[j], j0 + 1);
+    f[j] = fmaf(fy, v1, fmaf(1.0f - fy, v0, f[j]));
+  }
+}
+
+// u[i][j] = sum_c F[c][4 tp + i] * B[c][4 tm + j]     (fp32 FFMA, 4x4 register tile, operands from shared memory)
+__device__ __forceinline__ void fourier_project(const float* sF, const float* sBm, int tp, int tm, float (*u)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[i][j] = 0.f;
+#pragma unroll 8
+  for (int c = 0; c < F; ++c) {
+    const float4 f4 = *reinterpret_cast<const float4*>(sF + c * FLD + tp * 4);
+    const float4 b4 = *reinterpret_cast<const float4*>(sBm + c * MF + tm * 4);
+    const float fr[4] = {f4.x, f4.y, f4.z, f4.w};
+    const float br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[i][j] = fmaf(fr[i], br[j], u[i][j]);
+  }
 }
 
 template <bool GRID>
@@ -214,7 +345,7 @@ triplane_decode_tc_kernel(const Args a) {
     mbar_init(smem_u32(&bar_d), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -225,9 +356,11 @@ triplane_decode_tc_kernel(const Args a) {
   const uint32_t tmem = tmem_slot;
   const uint32_t a_hi = base + OFF_AH, a_lo = base + OFF_AL;
   const long long ntiles = (a.npts + TP - 1) / TP;
-  const size_t plane_sz = static_cast<size_t>(a.R) * a.R * F;
+  // contiguous tile range per CTA: consecutive tiles walk z, then y — the xz-plane rows of a z range are reused from L1
+  // for every y, only the yz-plane rows are new per tile
+  const long long tile_begin = ntiles * blockIdx.x / gridDim.x, tile_end = ntiles * (blockIdx.x + 1) / gridDim.x;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ===== MMA issuer =====
     if (lane == 0) {
       // instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128
@@ -235,7 +368,7 @@ triplane_decode_tc_kernel(const Args a) {
       const uint64_t d_ah = make_desc_sw128(a_hi), d_al = make_desc_sw128(a_lo);
       const uint32_t ba = smem_u32(&bar_a), bd = smem_u32(&bar_d);
       uint32_t ph = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (long long tile = tile_begin; tile < tile_end; ++tile) {
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           mbar_wait(ba, ph);
@@ -258,85 +391,74 @@ triplane_decode_tc_kernel(const Args a) {
     }
   } else {
     // ===== compute warps =====
+    // Software pipeline: while the tensor cores chew layer 1 of tile i the compute warps SAMPLE tile i+1, while they
+    // chew layer 2 the warps PROJECT tile i+1 onto the Fourier frequencies (u stays in registers across the epilogue).
     const uint32_t ba = smem_u32(&bar_a), bd = smem_u32(&bar_d);
     uint32_t phd = 0;
-    const int pt = tid >> 1, half = tid & 1;
-    const int q = warp & 3, colh = warp >> 2;            // TMEM lane quarter / column half of this warp
-    const int row = q * 32 + lane;
+    const int s_pt = (warp & 3) * 32 + lane, s_c0 = (warp >> 2) * 8;   // sampling: point, first of 8 channels
+    const int tp = tid >> 4, tm = tid & 15;                            // Fourier: points 4tp.., frequencies 4tm..
+    const int q = warp & 3, cg = warp >> 2;                            // TMEM lane quarter / 32-column group
+    const int row = q * 32 + lane, col0 = cg * 32;
     const float two_pi = 6.283185307179586f;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      // ---- P1: plane samples, 16 channels per thread ----
-      {
-        const long long i = tile * TP + pt;
-        float f[16];
+    float u[4][4];
+    {
+      float f[8];
+      if (GRID && a.fast_rows) sample_rows_fast(a, tile_begin, warp & 3, lane, s_c0, f);
+      else sample_point<GRID>(a, tile_begin, s_pt, s_c0, f);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = 0.f;
-        if (i < a.npts) {
-          float cx, cy, cz;
-          if (GRID) {
-            const long long gi = a.idx0 + i;
-            const int z = static_cast<int>(gi % a.res);
-            const long long t = gi / a.res;
-            const int y = static_cast<int>(t % a.res);
-            const int x = static_cast<int>(t / a.res);
-            cx = __ldg(a.lin + x); cy = __ldg(a.lin + y); cz = __ldg(a.lin + z);
-          } else {
-            cx = __ldg(a.coords + i * 3); cy = __ldg(a.coords + i * 3 + 1); cz = __ldg(a.coords + i * 3 + 2);
-          }
-          const int c0 = half * 16;
-          sample_plane16(a.planes, a.R, cx, cy, c0, f);                 // xy plane: x->W, y->H
-          sample_plane16(a.planes + plane_sz, a.R, cy, cz, c0, f);      // yz plane
-          sample_plane16(a.planes + 2 * plane_sz, a.R, cx, cz, c0, f);  // xz plane
-        }
+      for (int j = 0; j < 8; ++j) sF[(s_c0 + j) * FLD + s_pt] = f[j];
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      fourier_project(sF, sBm, tp, tm, u);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+    for (long long tile = tile_begin; tile < tile_end; ++tile) {
+      const long long next = tile + 1;
+      const bool has_next = next < tile_end;               // CTA-uniform
+      // ---- S0: [sin | cos](2 pi u) -> layer-1 operand (4 points x 4 frequencies per thread) ----
 #pragma unroll
-        for (int j = 0; j < 16; ++j) sF[pt * 33 + half * 16 + j] = f[j];
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      // ---- P2: Fourier features of 32 frequencies per thread -> layer-1 operand ----
-      {
-        float u[32];
+      for (int i = 0; i < 4; ++i) {
+        float sv[4], cv[4];
 #pragma unroll
-        for (int m = 0; m < 32; ++m) u[m] = 0.f;
-        const float* bm = sBm + half * 32;
-#pragma unroll 4
-        for (int c = 0; c < F; ++c) {
-          const float fc = sF[pt * 33 + c];
-#pragma unroll
-          for (int m4 = 0; m4 < 8; ++m4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bm + c * MF + m4 * 4);
-            u[4 * m4] = fmaf(fc, b4.x, u[4 * m4]); u[4 * m4 + 1] = fmaf(fc, b4.y, u[4 * m4 + 1]);
-            u[4 * m4 + 2] = fmaf(fc, b4.z, u[4 * m4 + 2]); u[4 * m4 + 3] = fmaf(fc, b4.w, u[4 * m4 + 3]);
-          }
-        }
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          float sv[8], cv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sincosf(two_pi * u[g8 * 8 + j], &sv[j], &cv[j]);
-          store_chunk(a_hi, a_lo, pt, half * 4 + g8, sv);            // k = m            (sin)
-          store_chunk(a_hi, a_lo, pt, 8 + half * 4 + g8, cv);        // k = 64 + m       (cos)
-        }
+        for (int j = 0; j < 4; ++j) sincos_cw(two_pi * u[i][j], sv[j], cv[j]);
+        const int r = tp * 4 + i;
+        uint32_t h0, h1, l0, l1;
+        const uint32_t off = chunk_off(r, tm >> 1) + static_cast<uint32_t>((tm & 1) * 8);
+        split2(sv[0], sv[1], h0, l0); split2(sv[2], sv[3], h1, l1);                 // k = 4 tm + j       (sin)
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + off), "r"(h0), "r"(h1) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo + off), "r"(l0), "r"(l1) : "memory");
+        split2(cv[0], cv[1], h0, l0); split2(cv[2], cv[3], h1, l1);                 // k = 64 + 4 tm + j  (cos)
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + ATOM + off), "r"(h0), "r"(h1) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo + ATOM + off), "r"(l0), "r"(l1) : "memory");
       }
       fence_async_smem();
       mbar_arrive(ba);
-      // ---- P3: h1 = relu(D1 + 2^-11 D1' + b1) -> layer-2 operand ----
+      // ---- S1 (under MMA layer 1): sample the next tile ----
+      if (has_next) {
+        float f[8];
+        if (GRID && a.fast_rows) sample_rows_fast(a, next, warp & 3, lane, s_c0, f);
+        else sample_point<GRID>(a, next, s_pt, s_c0, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sF[(s_c0 + j) * FLD + s_pt] = f[j];      // everyone left fourier_project long ago
+      }
+      // ---- S2: h1 = relu(D1 + 2^-11 D1' + b1) -> layer-2 operand ----
       mbar_wait(bd, phd);
       phd ^= 1u;
       fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        const int col0 = colh * 64 + c * 32;
+      {
         float d[32], dl[32];
         tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(col0), d);
         tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(128 + col0), dl);
         tmem_ld_wait();
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
+          const float4 ba4 = *reinterpret_cast<const float4*>(sb1 + col0 + g8 * 8);
+          const float4 bb4 = *reinterpret_cast<const float4*>(sb1 + col0 + g8 * 8 + 4);
+          const float bv[8] = {ba4.x, ba4.y, ba4.z, ba4.w, bb4.x, bb4.y, bb4.z, bb4.w};
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = g8 * 8 + j;
-            v[j] = fmaxf(fmaf(dl[k], 1.0f / 2048.0f, d[k]) + sb1[col0 + k], 0.f);
+            v[j] = fmaxf(fmaf(dl[k], 1.0f / 2048.0f, d[k]) + bv[j], 0.f);
           }
           store_chunk(a_hi, a_lo, row, (col0 >> 3) + g8, v);
         }
@@ -344,35 +466,42 @@ triplane_decode_tc_kernel(const Args a) {
       fence_async_smem();
       fence_before();
       mbar_arrive(ba);
-      // ---- P4: logit = w3 . relu(D2 + 2^-11 D2' + b2) + b3 ----
+      // ---- S3 (under MMA layer 2): Fourier projection of the next tile ----
+      asm volatile("bar.sync 1, 512;" ::: "memory");          // sF of the next tile is complete
+      if (has_next) fourier_project(sF, sBm, tp, tm, u);
+      // ---- S4: logit = w3 . relu(D2 + 2^-11 D2' + b2) + b3 ----
       mbar_wait(bd, phd);
       phd ^= 1u;
       fence_after();
       float acc = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        const int col0 = colh * 64 + c * 32;
+      {
         float d[32], dl[32];
         tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(256 + col0), d);
         tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(384 + col0), dl);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k)
-          acc = fmaf(sw3[col0 + k], fmaxf(fmaf(dl[k], 1.0f / 2048.0f, d[k]) + sb2[col0 + k], 0.f), acc);
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(sw3 + col0 + k4 * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(sb2 + col0 + k4 * 4);
+          const int k = k4 * 4;
+          acc = fmaf(w4.x, fmaxf(fmaf(dl[k], 1.0f / 2048.0f, d[k]) + b4.x, 0.f), acc);
+          acc = fmaf(w4.y, fmaxf(fmaf(dl[k + 1], 1.0f / 2048.0f, d[k + 1]) + b4.y, 0.f), acc);
+          acc = fmaf(w4.z, fmaxf(fmaf(dl[k + 2], 1.0f / 2048.0f, d[k + 2]) + b4.z, 0.f), acc);
+          acc = fmaf(w4.w, fmaxf(fmaf(dl[k + 3], 1.0f / 2048.0f, d[k + 3]) + b4.w, 0.f), acc);
+        }
       }
       fence_before();
-      if (colh == 1) sx[row] = acc;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (colh == 0) {
+      if (cg > 0) sx[(cg - 1) * TP + row] = acc;
+      asm volatile("bar.sync 1, 512;" ::: "memory");          // also: every thread is past fourier_project (sF reusable)
+      if (cg == 0) {
         const long long i = tile * TP + row;
-        if (i < a.npts) a.out[i] = (acc + sx[row]) + b3;
+        if (i < a.npts) a.out[i] = (((acc + sx[row]) + sx[TP + row]) + sx[2 * TP + row]) + b3;
       }
-      // (the next tile's P1 writes sF only; sx is rewritten after the next bar.sync 1 pair)
     }
   }
   fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
@@ -390,7 +519,9 @@ bool decode_tc_usable(float h1_bound) { return h1_bound > 0.f && h1_bound <= 300
 
 int decode_tc_launch(const float* planes, int R, const isb_triplane_mlp* w, const float* lin, int res, long long idx0,
                      const float* coords, long long npts, float* out, bool grid_mode, cudaStream_t st) {
-  dtc::Args a{planes, R, w->fourier_B, w->w1, w->b1, w->w2, w->b2, w->w3, w->b3, lin, res, idx0, coords, npts, out};
+  dtc::Args a{planes, R, w->fourier_B, w->w1, w->b1, w->w2, w->b2, w->w3, w->b3, lin, res, idx0, coords, npts, out, 0};
+  // cooperative row sampling: whole tiles share (x, y), and the 32 z of a warp touch at most 31 plane rows
+  if (grid_mode && res % dtc::TP == 0 && idx0 % dtc::TP == 0 && 31.0 * (R - 1) / (res - 1) + 2.0 <= 31.0) a.fast_rows = 1;
   const long long ntiles = (npts + dtc::TP - 1) / dtc::TP;
   const long long blocks = ntiles < num_sms() ? ntiles : num_sms();
   if (blocks < 1) return ISB_OK;
