@@ -37,13 +37,14 @@ constexpr int COMPUTE_THREADS = 512;    // 16 compute warps: 4 per TMEM lane qua
 constexpr int THREADS = COMPUTE_THREADS + 32;
 constexpr int ATOM = TP * 128;          // one K-atom: 128 rows x 64 fp16 = 16 KiB
 constexpr int OPER = 2 * ATOM;          // one 128x128 fp16 operand = 32 KiB
-constexpr int FLD = TP + 4;             // row pitch of the transposed feature staging F[c][pt]
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int OFF_W1H = 0, OFF_W1L = OPER, OFF_W2H = 2 * OPER, OFF_W2L = 3 * OPER;
 constexpr int OFF_AH = 4 * OPER, OFF_AL = 5 * OPER;
-constexpr int OFF_F = 6 * OPER;                      // float F[32][132]
-constexpr int OFF_BM = OFF_F + F * FLD * 4;          // float Bm[32][64]
-constexpr int OFF_VEC = OFF_BM + F * MF * 4;         // float b1[128], b2[128], w3[128]
+constexpr int OFF_FOP = 6 * OPER;                    // plane features as a UMMA A operand: 128 rows x 64 fp16,
+                                                     //   k 0..31 = f_hi, k 32..63 = f_lo' (one 16 KiB atom)
+constexpr int OFF_BOP = OFF_FOP + ATOM;              // Fourier matrix as a B operand: 64 rows (frequencies) x 64 fp16,
+                                                     //   k 0..31 = B_hi^T, k 32..63 = B_lo'^T (8 KiB)
+constexpr int OFF_VEC = OFF_BOP + MF * 128;          // float b1[128], b2[128], w3[128]
 constexpr int OFF_X = OFF_VEC + 3 * H * 4;           // float xch[3][128]
 constexpr int SMEM_BYTES = OFF_X + 3 * TP * 4 + 1024;  // + alignment slack
 
@@ -277,23 +278,30 @@ __device__ __forceinline__ void sample_rows_fast(const Args& a, long long tile, 
   }
 }
 
-// u[i][j] = sum_c F[c][4 tp + i] * B[c][4 tm + j]     (fp32 FFMA, 4x4 register tile, operands from shared memory)
-__device__ __forceinline__ void fourier_project(const float* sF, const float* sBm, int tp, int tm, float (*u)[4]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// 8 plane features of one point -> f_hi (k = c0..c0+7) and f_lo' = (f - f_hi) * 2^11 (k = 32 + c0..) of the F operand
+__device__ __forceinline__ void store_features(uint32_t fop, int r, int c0, const float* f) {
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) u[i][j] = 0.f;
-#pragma unroll 8
-  for (int c = 0; c < F; ++c) {
-    const float4 f4 = *reinterpret_cast<const float4*>(sF + c * FLD + tp * 4);
-    const float4 b4 = *reinterpret_cast<const float4*>(sBm + c * MF + tm * 4);
-    const float fr[4] = {f4.x, f4.y, f4.z, f4.w};
-    const float br[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) u[i][j] = fmaf(fr[i], br[j], u[i][j]);
+  for (int j = 0; j < 4; ++j) {
+    const __half h0 = __float2half_rn(f[2 * j]), h1 = __float2half_rn(f[2 * j + 1]);
+    const __half l0 = __float2half_rn((f[2 * j] - __half2float(h0)) * 2048.0f);
+    const __half l1 = __float2half_rn((f[2 * j + 1] - __half2float(h1)) * 2048.0f);
+    h[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+    l[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
   }
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(fop + chunk_off(r, c0 >> 3)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(fop + chunk_off(r, 4 + (c0 >> 3))), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
 }
 
 template <bool GRID>
@@ -302,12 +310,10 @@ triplane_decode_tc_kernel(const Args a) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_a, bar_d;
+  __shared__ __align__(8) uint64_t bar_a, bar_d, bar_u;
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  float* sF = reinterpret_cast<float*>(gbase + OFF_F);
-  float* sBm = reinterpret_cast<float*>(gbase + OFF_BM);
   float* sb1 = reinterpret_cast<float*>(gbase + OFF_VEC);
   float* sb2 = sb1 + H;
   float* sw3 = sb2 + H;
@@ -337,12 +343,27 @@ triplane_decode_tc_kernel(const Args a) {
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dl), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
     }
   }
-  for (int i = tid; i < F * MF; i += THREADS) sBm[i] = __ldg(a.fourier_B + i);
+  for (int i = tid; i < MF * (F / 8); i += THREADS) {           // Fourier matrix B[c][m] -> operand rows m, k = c
+    const int m = i / (F / 8), k8 = i % (F / 8);
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v0 = __ldg(a.fourier_B + (k8 * 8 + 2 * j) * MF + m), v1 = __ldg(a.fourier_B + (k8 * 8 + 2 * j + 1) * MF + m);
+      const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+      const __half l0 = __float2half_rn((v0 - __half2float(h0)) * 2048.0f), l1 = __float2half_rn((v1 - __half2float(h1)) * 2048.0f);
+      h[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+      l[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+    }
+    const uint32_t bop = base + OFF_BOP;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bop + chunk_off(m, k8)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bop + chunk_off(m, 4 + k8)), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+  }
   if (tid < H) { sb1[tid] = __ldg(a.b1 + tid); sb2[tid] = __ldg(a.b2 + tid); sw3[tid] = __ldg(a.w3 + tid); }
   const float b3 = __ldg(a.b3);
   if (tid == 0) {
     mbar_init(smem_u32(&bar_a), COMPUTE_THREADS);
     mbar_init(smem_u32(&bar_d), 1);
+    mbar_init(smem_u32(&bar_u), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 16) {
@@ -366,8 +387,28 @@ triplane_decode_tc_kernel(const Args a) {
       // instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128
       const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(H >> 3) << 17) | (static_cast<uint32_t>(TP >> 4) << 24);
       const uint64_t d_ah = make_desc_sw128(a_hi), d_al = make_desc_sw128(a_lo);
-      const uint32_t ba = smem_u32(&bar_a), bd = smem_u32(&bar_d);
+      // Fourier projection u = f @ B on the tensor cores too: M = 128, N = 64, K = 32 per term
+      const uint32_t idesc_u = (1u << 4) | (static_cast<uint32_t>(MF >> 3) << 17) | (static_cast<uint32_t>(TP >> 4) << 24);
+      const uint64_t d_f = make_desc_sw128(base + OFF_FOP), d_b = make_desc_sw128(base + OFF_BOP);
+      const uint32_t ba = smem_u32(&bar_a), bd = smem_u32(&bar_d), bu = smem_u32(&bar_u);
       uint32_t ph = 0;
+      auto fourier_mma = [&]() {
+        // u (D1 columns 0..63) = f_hi B_hi^T;   u' (D1' columns 0..63) = f_hi B_lo'^T + f_lo' B_hi^T   (u = u + 2^-11 u')
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t hi = static_cast<uint64_t>(ks * 2), lo = static_cast<uint64_t>(4 + ks * 2);
+          umma_f16(tmem + 128u, d_f + hi, d_b + lo, idesc_u, ks > 0 ? 1u : 0u);
+          umma_f16(tmem + 128u, d_f + lo, d_b + hi, idesc_u, 1u);
+          umma_f16(tmem, d_f + hi, d_b + hi, idesc_u, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(bu);
+      };
+      if (tile_begin < tile_end) {                 // prologue: the first tile's features are in place
+        mbar_wait(ba, ph);
+        ph ^= 1u;
+        fence_after();
+        fourier_mma();
+      }
       for (long long tile = tile_begin; tile < tile_end; ++tile) {
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
@@ -386,6 +427,9 @@ triplane_decode_tc_kernel(const Args a) {
             umma_f16(dmain, d_ah + ko, d_wh + ko, idesc, 1u);
           }
           umma_commit(bd);
+          // D1 / D1' were drained by the layer-1 epilogue and the next tile's features were staged before it: project
+          // them while the compute warps run the layer-2 epilogue
+          if (layer == 1 && tile + 1 < tile_end) fourier_mma();
         }
       }
     }
@@ -393,52 +437,53 @@ triplane_decode_tc_kernel(const Args a) {
     // ===== compute warps =====
     // Software pipeline: while the tensor cores chew layer 1 of tile i the compute warps SAMPLE tile i+1, while they
     // chew layer 2 the warps PROJECT tile i+1 onto the Fourier frequencies (u stays in registers across the epilogue).
-    const uint32_t ba = smem_u32(&bar_a), bd = smem_u32(&bar_d);
-    uint32_t phd = 0;
+    const uint32_t ba = smem_u32(&bar_a), bd = smem_u32(&bar_d), bu = smem_u32(&bar_u);
+    const uint32_t fop = base + OFF_FOP;
+    uint32_t phd = 0, phu = 0;
     const int s_pt = (warp & 3) * 32 + lane, s_c0 = (warp >> 2) * 8;   // sampling: point, first of 8 channels
-    const int tp = tid >> 4, tm = tid & 15;                            // Fourier: points 4tp.., frequencies 4tm..
-    const int q = warp & 3, cg = warp >> 2;                            // TMEM lane quarter / 32-column group
+    const int q = warp & 3, cg = warp >> 2;                            // TMEM lane quarter / column group
     const int row = q * 32 + lane, col0 = cg * 32;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
     const float two_pi = 6.283185307179586f;
-    float u[4][4];
-    {
+    if (tile_begin < tile_end) {           // prologue: features of the first tile -> F operand -> first projection
       float f[8];
       if (GRID && a.fast_rows) sample_rows_fast(a, tile_begin, warp & 3, lane, s_c0, f);
       else sample_point<GRID>(a, tile_begin, s_pt, s_c0, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sF[(s_c0 + j) * FLD + s_pt] = f[j];
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      fourier_project(sF, sBm, tp, tm, u);
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      store_features(fop, s_pt, s_c0, f);
+      fence_async_smem();
+      mbar_arrive(ba);
     }
     for (long long tile = tile_begin; tile < tile_end; ++tile) {
       const long long next = tile + 1;
       const bool has_next = next < tile_end;               // CTA-uniform
-      // ---- S0: [sin | cos](2 pi u) -> layer-1 operand (4 points x 4 frequencies per thread) ----
+      // ---- S0: u = D + 2^-11 D' (Fourier projection, 16 frequencies of this thread's point) -> [sin | cos](2 pi u)
+      //          -> layer-1 operand ----
+      mbar_wait(bu, phu);
+      phu ^= 1u;
+      fence_after();
+      {
+        float d[16], dl[16];
+        tmem_ld16(trow + static_cast<uint32_t>(cg * 16), d);
+        tmem_ld16(trow + static_cast<uint32_t>(128 + cg * 16), dl);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float sv[4], cv[4];
+        for (int g8 = 0; g8 < 2; ++g8) {
+          float sv[8], cv[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sincos_cw(two_pi * u[i][j], sv[j], cv[j]);
-        const int r = tp * 4 + i;
-        uint32_t h0, h1, l0, l1;
-        const uint32_t off = chunk_off(r, tm >> 1) + static_cast<uint32_t>((tm & 1) * 8);
-        split2(sv[0], sv[1], h0, l0); split2(sv[2], sv[3], h1, l1);                 // k = 4 tm + j       (sin)
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + off), "r"(h0), "r"(h1) : "memory");
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo + off), "r"(l0), "r"(l1) : "memory");
-        split2(cv[0], cv[1], h0, l0); split2(cv[2], cv[3], h1, l1);                 // k = 64 + 4 tm + j  (cos)
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + ATOM + off), "r"(h0), "r"(h1) : "memory");
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo + ATOM + off), "r"(l0), "r"(l1) : "memory");
+          for (int j = 0; j < 8; ++j) sincos_cw(two_pi * fmaf(dl[g8 * 8 + j], 1.0f / 2048.0f, d[g8 * 8 + j]), sv[j], cv[j]);
+          store_chunk(a_hi, a_lo, row, cg * 2 + g8, sv);            // k = m          (sin), m = 16 cg + 8 g8 + j
+          store_chunk(a_hi, a_lo, row, 8 + cg * 2 + g8, cv);        // k = 64 + m     (cos)
+        }
       }
       fence_async_smem();
+      fence_before();
       mbar_arrive(ba);
-      // ---- S1 (under MMA layer 1): sample the next tile ----
+      // ---- S1 (under MMA layer 1): sample the next tile into the F operand (its projection was consumed above) ----
       if (has_next) {
         float f[8];
         if (GRID && a.fast_rows) sample_rows_fast(a, next, warp & 3, lane, s_c0, f);
         else sample_point<GRID>(a, next, s_pt, s_c0, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sF[(s_c0 + j) * FLD + s_pt] = f[j];      // everyone left fourier_project long ago
+        store_features(fop, s_pt, s_c0, f);
       }
       // ---- S2: h1 = relu(D1 + 2^-11 D1' + b1) -> layer-2 operand ----
       mbar_wait(bd, phd);
@@ -446,8 +491,8 @@ triplane_decode_tc_kernel(const Args a) {
       fence_after();
       {
         float d[32], dl[32];
-        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(col0), d);
-        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(128 + col0), dl);
+        tmem_ld32(trow + static_cast<uint32_t>(col0), d);
+        tmem_ld32(trow + static_cast<uint32_t>(128 + col0), dl);
         tmem_ld_wait();
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
@@ -463,12 +508,9 @@ triplane_decode_tc_kernel(const Args a) {
           store_chunk(a_hi, a_lo, row, (col0 >> 3) + g8, v);
         }
       }
-      fence_async_smem();
+      fence_async_smem();          // covers the layer-2 operand AND the next tile's F operand (S1)
       fence_before();
       mbar_arrive(ba);
-      // ---- S3 (under MMA layer 2): Fourier projection of the next tile ----
-      asm volatile("bar.sync 1, 512;" ::: "memory");          // sF of the next tile is complete
-      if (has_next) fourier_project(sF, sBm, tp, tm, u);
       // ---- S4: logit = w3 . relu(D2 + 2^-11 D2' + b2) + b3 ----
       mbar_wait(bd, phd);
       phd ^= 1u;
@@ -476,8 +518,8 @@ triplane_decode_tc_kernel(const Args a) {
       float acc = 0.f;
       {
         float d[32], dl[32];
-        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(256 + col0), d);
-        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(384 + col0), dl);
+        tmem_ld32(trow + static_cast<uint32_t>(256 + col0), d);
+        tmem_ld32(trow + static_cast<uint32_t>(384 + col0), dl);
         tmem_ld_wait();
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
@@ -492,11 +534,12 @@ triplane_decode_tc_kernel(const Args a) {
       }
       fence_before();
       if (cg > 0) sx[(cg - 1) * TP + row] = acc;
-      asm volatile("bar.sync 1, 512;" ::: "memory");          // also: every thread is past fourier_project (sF reusable)
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       if (cg == 0) {
         const long long i = tile * TP + row;
         if (i < a.npts) a.out[i] = (((acc + sx[row]) + sx[TP + row]) + sx[2 * TP + row]) + b3;
       }
+      // (sx is rewritten only after the next tile's barriers: every reader is long past this point)
     }
   }
   fence_before();
