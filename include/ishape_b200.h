@@ -344,6 +344,31 @@ int isb_triplane_decode_points_backward(const float* planes_hwc, int R, const is
                                         const float* coords, int64_t npts, const float* d_logits,
                                         float* d_planes_hwc, isb_stream_t stream);
 
+/* ---- meshing tail of the decode path -------------- */
+/* Marching cubes over the logit volume vol[res][res][res] (x-major, as isb_triplane_decode_grid writes it), replacing
+ * `mcubes.marching_cubes(pred, 0)` + `vertices / res * 2 - 1` (triplane_decoder/visualize.py:100-101).  Two calls,
+ * because the output size is data-dependent:
+ *   isb_mc_count  classifies every cell / grid edge and scans; counts[0] = vertices, counts[1] = triangles (DEVICE
+ *                 int64[2]; the caller reads them back and allocates);
+ *   isb_mc_emit   writes verts [nv,3] fp32 and tris [nt,3] int32 using the SAME workspace.
+ * One shared vertex per crossed grid edge (linear interpolation, IEEE fp32 ops); vertex order = grid point (x-major)
+ * then edge axis, triangle order = cell (x-major) then case-table order: deterministic, no atomics.
+ * scale_div > 0: vertices are written as v / scale_div * 2 - 1 (the reference passes res); 0: index coordinates as
+ * PyMCubes returns them.  Case bit i = value(corner i) < iso, Bourke corner / edge numbering; the table is derived in
+ * ishapediting_b200/triplane_decoder/mc_table.py (PyMCubes is an un-pinned dependency not installed offline: parity
+ * with that binary is unpinned; the CPU checker is oracle/mcubes_oracle.py). */
+size_t isb_mc_workspace_bytes(int res);
+int isb_mc_count(const float* vol, int res, float iso, void* workspace, size_t workspace_bytes, int64_t* counts,
+                 isb_stream_t stream);
+int isb_mc_emit(const float* vol, int res, float iso, void* workspace, size_t workspace_bytes, float scale_div,
+                float* verts, int32_t* tris, isb_stream_t stream);
+/* Open3D TriangleMesh::FilterSmoothSimple (`filter_smooth_simple(number_of_iterations=10)`, drag_utils.py:300):
+ * `iterations` times v_i <- (v_i + sum_{j in N(i)} v_j) / (1 + |N(i)|), N(i) = vertices sharing a triangle edge with i,
+ * every vertex updated from the previous iterate, float64 arithmetic (as Open3D), verts [nv,3] fp32 in place. */
+size_t isb_mesh_smooth_workspace_bytes(int64_t nv, int64_t nt);
+int isb_mesh_smooth_simple(float* verts, int64_t nv, const int32_t* tris, int64_t nt, int iterations,
+                           void* workspace, size_t workspace_bytes, isb_stream_t stream);
+
 /* ---- introspection ---------------------------------------------------- */
 /* Number of kernels this library has launched in this process (all threads). */
 uint64_t isb_launch_count(void);

@@ -47,6 +47,7 @@ tensormap_encode_fn get_tensormap_encode() { return g_encode; }
 int conv_tc_init();     // conv_tc.cu: raise dynamic smem limit
 void conv_tc_set_trace(void* ptr);
 int decode_init();      // decode.cu
+int mc_init();          // mc.cu: case table -> constant memory
 int attention_flash_init();   // attention_flash.cu
 
 // profiling only: a chain of n dependent, (almost) empty kernels — the floor of one dependent launch in a stream /
@@ -110,6 +111,8 @@ int isb_init(int device) {
     isb::g_encode = reinterpret_cast<isb::tensormap_encode_fn>(fn);
   }
   int rc = isb::conv_tc_init();
+  if (rc) return rc;
+  rc = isb::mc_init();
   if (rc) return rc;
   rc = isb::decode_init();
   if (rc) return rc;

@@ -59,6 +59,11 @@ def get_args(argv=None):
         rescale_learned_sigmas=False)
 
 
+def _copy_mesh(m):
+    """The reference deep-copies its Open3D meshes (:279,564); device meshes / volumes are cloned."""
+    return m.clone() if hasattr(m, "clone") else copy.deepcopy(m)
+
+
 def make_offsets(r, device):
     p = th.arange(-r, r + 1, device=device)
     px, py, pz = th.meshgrid(p, p, p, indexing="ij")
@@ -580,6 +585,9 @@ class DragStuff:
         self.feature_guidance = []       # device tensors, channels-last (3,S,S,Ca); see feature_guidance_nchw()
         self.use_graph = use_graph
         self.last_volume = None
+        # True (default): get_mesh returns the smoothed triangle mesh like the reference (marching cubes + 10 Laplacian
+        # iterations, on the device); False: it stops at the logit volume (benchmark legs that time the decode alone)
+        self.mesh_on_device = True
 
     def set_offset1(self, r1):
         self.r1 = r1
@@ -664,7 +672,7 @@ class DragStuff:
                                                                             plan.ops.empty((3, S, S, Ca))))
             assert len(self.feature_guidance) == self.args.w_time
             self.mesh0 = self.get_mesh(tri_feat=img)
-            self.mesh = copy.deepcopy(self.mesh0) if not th.is_tensor(self.mesh0) else self.mesh0.clone()
+            self.mesh = _copy_mesh(self.mesh0)
             return img
 
     # ---- decode (reference :282-300) -----------------------------------------------------------------
@@ -680,11 +688,12 @@ class DragStuff:
             tri_feat = (tri_feat * self.range + self.middle).reshape(3, 32, R, R)
             for i in range(3):
                 self.decoder.embeddings[i] = tri_feat[[i]]
-            self.last_volume = query_volume(self.decoder, 0, res=self.args.shape_resolution)
-            mesh = create_obj_o3d(self.decoder, 0, res=self.args.shape_resolution) if _have_meshing() else self.last_volume
-            if hasattr(mesh, "filter_smooth_simple"):
-                return mesh.filter_smooth_simple(number_of_iterations=10)
-            return mesh
+            res = self.args.shape_resolution
+            self.last_volume = query_volume(self.decoder, 0, res=res)           # decoded ONCE; meshed from this volume
+            if not self.mesh_on_device:
+                return self.last_volume
+            mesh = create_obj_o3d(self.decoder, 0, res=res, volume=self.last_volume)
+            return mesh.filter_smooth_simple(number_of_iterations=10)           # reference :300
 
     # ---- real-shape reconstruction guidance (reference :400-471) ---------------------------
     def recon_guided_step(self, img, i, coords, gt, scale=600.0, noise=None):
@@ -716,7 +725,7 @@ class DragStuff:
             img = st.img.clone()
         self.clear_params()
         self.mesh = self.get_mesh(tri_feat=img)
-        self.mesh0 = copy.deepcopy(self.mesh) if not th.is_tensor(self.mesh) else self.mesh.clone()
+        self.mesh0 = _copy_mesh(self.mesh)
         return img
 
     # ---- the guided edit (reference :302-399) -----------------------------------------------------------
@@ -771,7 +780,7 @@ class DragStuff:
         self.w0 = self.w.clone().detach()
         self.feature_guidance = [resize_feat_align(f).permute(0, 2, 3, 1).contiguous() for f in outs["inter_feat"]]
         self.mesh = self.get_mesh(tri_feat=outs["sample"])
-        self.mesh0 = copy.deepcopy(self.mesh) if not th.is_tensor(self.mesh) else self.mesh.clone()
+        self.mesh0 = _copy_mesh(self.mesh)
         self.variance = [v.clone().detach() for v in outs["variance"]]
         self.variance_noise = [v.clone().detach() for v in outs["variance_noise"]]
 
@@ -788,15 +797,6 @@ class DragStuff:
 
     def reset_params(self):
         if self.mesh is not None:
-            self.mesh = copy.deepcopy(self.mesh0) if not th.is_tensor(self.mesh0) else self.mesh0.clone()
+            self.mesh = _copy_mesh(self.mesh0)
         if self.w0 is not None:
             self.w = self.w0.clone().detach()
-
-
-def _have_meshing():
-    try:
-        import mcubes  # noqa: F401
-        import open3d  # noqa: F401
-        return True
-    except ImportError:
-        return False

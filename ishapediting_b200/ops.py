@@ -420,6 +420,37 @@ class CudaOps:
         _lib.check(self.lib.isb_track_points(C.byref(d), _stream()), "isb_track_points")
         return idx, dist, pts, table
 
+    # ---- meshing (marching cubes + Laplacian smoothing) ------------------------------------------
+    def marching_cubes(self, vol, iso=0.0, scale_div=0.0):
+        """vol (res,res,res) fp32 -> (verts [nv,3] fp32, tris [nt,3] int32) on the device (isb_mc_count / isb_mc_emit).
+        One host read-back of the two counts (the output size is data-dependent)."""
+        _chk(vol, torch.float32)
+        res = vol.shape[0]
+        assert tuple(vol.shape) == (res, res, res)
+        nbytes = int(self.lib.isb_mc_workspace_bytes(res))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.isb_mc_count(_p(vol), res, float(iso), _p(ws), nbytes, _p(counts), _stream()), "isb_mc_count")
+        nv, nt = (int(v) for v in counts.tolist())
+        verts = torch.empty((nv, 3), dtype=torch.float32, device=self.device)
+        tris = torch.empty((nt, 3), dtype=torch.int32, device=self.device)
+        if nv or nt:
+            _lib.check(self.lib.isb_mc_emit(_p(vol), res, float(iso), _p(ws), nbytes, float(scale_div), _p(verts), _p(tris),
+                                            _stream()), "isb_mc_emit")
+        return verts, tris
+
+    def smooth_simple(self, verts, tris, iterations):
+        """In-place uniform Laplacian smoothing (isb_mesh_smooth_simple)."""
+        _chk(verts, torch.float32); _chk(tris, torch.int32)
+        nv, nt = verts.shape[0], tris.shape[0]
+        if nv == 0 or nt == 0 or iterations <= 0:
+            return verts
+        nbytes = int(self.lib.isb_mesh_smooth_workspace_bytes(nv, nt))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.isb_mesh_smooth_simple(_p(verts), nv, _p(tris), nt, int(iterations), _p(ws), nbytes, _stream()),
+                   "isb_mesh_smooth_simple")
+        return verts
+
     # ---- triplane decoder ---------------------------------------------------------------------
     def _mlp(self, weights):
         m = _lib.TriplaneMlp()

@@ -3,10 +3,8 @@
 The reference builds the (res^3, 3) coordinate tensor on the CPU, loops over 50 000-point chunks with
 a host<->device round trip per chunk, and meshes with PyMCubes.  Here the grid is generated inside
 the decode kernel, a contiguous x-slab [x_begin, x_end) can be requested (the multi-GPU shard, index =
-x*res^2 + y*res + z as in visualize.py:83-86) and the logit volume stays on the device.  Marching
-cubes / Open3D smoothing are CPU third-party code outside the hot path: if
-`mcubes` and `open3d` are installed the reference's meshing tail is reproduced, otherwise the volume
-is returned.
+x*res^2 + y*res + z as in visualize.py:83-86) and the logit volume stays on the device, where
+marching cubes and the Laplacian smoothing run too (marching_cubes.py, csrc/mc.cu).
 """
 import torch
 
@@ -25,18 +23,13 @@ def query_volume(model, obj_idx, res=128, x_begin=0, x_end=None, out=None):
     return out.view(x_end - x_begin, res, res)
 
 
-def create_obj_o3d(model, obj_idx, res=128, max_batch_size=50000):
-    """Reference signature; `max_batch_size` is accepted and ignored (no chunking is needed).
-    Returns an open3d TriangleMesh when mcubes+open3d are importable, else the logit volume."""
-    vol = query_volume(model, obj_idx, res)
-    try:
-        import mcubes
-        import open3d as o3d
-    except ImportError:
-        return vol
-    vertices, triangles = mcubes.marching_cubes(vol.cpu().numpy(), 0)
-    vertices = vertices / res * 2 - 1
-    mesh = o3d.geometry.TriangleMesh()
-    mesh.vertices = o3d.utility.Vector3dVector(vertices)
-    mesh.triangles = o3d.utility.Vector3iVector(triangles)
-    return mesh
+def create_obj_o3d(model, obj_idx, res=128, max_batch_size=50000, volume=None):
+    """Reference signature (visualize.py:76-105); `max_batch_size` is accepted and ignored (no chunking is needed).
+    Dense query -> marching cubes at 0 -> vertices / res * 2 - 1, all on the device; returns a
+    marching_cubes.TriangleMesh (`.vertices`, `.triangles`, `.filter_smooth_simple`, `.to_open3d()`).
+    `volume`: an already decoded (res,res,res) logit volume to mesh (get_mesh passes the one it just computed
+    instead of decoding twice)."""
+    from .marching_cubes import mesh_from_volume
+
+    vol = query_volume(model, obj_idx, res) if volume is None else volume
+    return mesh_from_volume(vol.reshape(res, res, res), res, 0.0, model._get_ops())
