@@ -325,6 +325,7 @@ def run_ours(args):
     a = get_args(["--num_steps", "200", "--w_time", str(W_TIME), "--shape_resolution", str(DECODE_RES)])
     a.use_fp16 = (args.mode == "bf16")
     ds = DragStuff(args=a, device=dev, use_graph=not args.no_graph)
+    ds.mesh_on_device = False        # configs[1] times the steps + the logit volume; meshing is its own leg below
     ds.model.load_state_dict(O.synth_state_dict(O.NFD_CFG))
     ds.model.to(dev).eval()
     w, planes = O.synth_decoder()
@@ -450,6 +451,19 @@ def run_ours(args):
         del vol
         torch.cuda.empty_cache()
 
+    # ---- meshing tail: marching cubes + 10 Laplacian iterations on the 256^3 volume ----
+    from ishapediting_b200.triplane_decoder.visualize import create_obj_o3d
+    vol256 = query_volume(ds.decoder, 0, DECODE_RES)
+    create_obj_o3d(ds.decoder, 0, res=DECODE_RES, volume=vol256).filter_smooth_simple(10)      # warm-up
+    ms_mc, mesh_dev = timed(lambda: create_obj_o3d(ds.decoder, 0, res=DECODE_RES, volume=vol256))
+    ms_smooth, _ = timed(lambda: mesh_dev.filter_smooth_simple(10))
+    mesh_leg = {"res": DECODE_RES, "vertices": int(mesh_dev.vertices.shape[0]), "triangles": int(mesh_dev.triangles.shape[0]),
+                "ms_marching_cubes": ms_mc, "ms_smooth_10_iterations": ms_smooth,
+                "what": "device marching cubes (incl. the read-back of the two counts) and filter_smooth_simple(10) on the "
+                        "synthetic 24 %-occupancy field; the reference runs PyMCubes / Open3D on the CPU here"}
+    del vol256, mesh_dev
+    torch.cuda.empty_cache()
+
     # ---- throughput mode: B independent edits advanced as one batch (configs[4], "batched" variant) ----
     batched = None
     if args.batch > 1:
@@ -509,6 +523,7 @@ def run_ours(args):
                               "ms_gather": ms_gather_edits, "gathered_ok": edits_ok,
                               "what": "BASELINE configs[4]: 8 edits per GPU dealt round-robin (parallel.assign_edits), "
                                       "final latents collected with one all_gather_into_tensor (parallel.gather_results)"},
+            "mesh": mesh_leg,
             "decode_sharded": dict(decode, what="BASELINE configs[3]: dense decode, x-slabs over the ranks written "
                                                 "straight into the full volume + one in-place all_gather_into_tensor; "
                                                 "times are max over ranks"),

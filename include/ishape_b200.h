@@ -369,6 +369,12 @@ size_t isb_mesh_smooth_workspace_bytes(int64_t nv, int64_t nt);
 int isb_mesh_smooth_simple(float* verts, int64_t nv, const int32_t* tris, int64_t nt, int iterations,
                            void* workspace, size_t workspace_bytes, isb_stream_t stream);
 
+/* ---- L2 prefetch -------------------------------------------------------- */
+/* Start pulling [ptr, ptr+bytes) into L2 (cp.async.bulk.prefetch.L2, one per 16 KiB) and return; the host layer
+ * uses it on a side stream to stream the weight panels of the NEXT layers while the current, latency-bound layer
+ * runs (HBM is idle ~95 % of a batch-1 step).  The reference has no counterpart: PyTorch eager issues no prefetch. */
+int isb_prefetch_l2(const void* ptr, size_t bytes, isb_stream_t stream);
+
 /* ---- introspection ---------------------------------------------------- */
 /* Number of kernels this library has launched in this process (all threads). */
 uint64_t isb_launch_count(void);

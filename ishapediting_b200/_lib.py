@@ -141,6 +141,7 @@ PROTOTYPES = {
     "isb_drag_loss_grad": (c_int, [C.POINTER(DragDesc), c_void_p]),
     "isb_resize_feat_align": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "isb_track_points": (c_int, [C.POINTER(TrackDesc), c_void_p]),
+    "isb_prefetch_l2": (c_int, [c_void_p, c_size_t, c_void_p]),
     "isb_mc_workspace_bytes": (c_size_t, [c_int]),
     "isb_mc_count": (c_int, [c_void_p, c_int, C.c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
     "isb_mc_emit": (c_int, [c_void_p, c_int, C.c_float, c_void_p, c_size_t, C.c_float, c_void_p, c_void_p, c_void_p]),

@@ -72,9 +72,39 @@ cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ 
   store8(dst, i * 8, ISB_BF16, v);
 }
 
+// L2 prefetch of a byte range (weight panels of layers a few launches ahead): one bulk prefetch per 16 KiB chunk.
+// The kernel only ISSUES the prefetches and exits; the data streams into L2 in the background.  No PDL wait: it reads
+// nothing that a predecessor produces (weights are constant for the life of a plan).
+constexpr size_t PF_CHUNK = 16384;
+__global__ void __launch_bounds__(128)
+prefetch_l2_kernel(const char* __restrict__ ptr, size_t bytes) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t off = i * PF_CHUNK;
+  if (off >= bytes) return;
+  size_t len = bytes - off;
+  if (len > PF_CHUNK) len = PF_CHUNK;
+  len &= ~static_cast<size_t>(15);
+  if (len == 0) return;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + off), "r"(static_cast<uint32_t>(len)) : "memory");
+}
+
 }  // namespace isb
 
 extern "C" {
+
+int isb_prefetch_l2(const void* ptr, size_t bytes, isb_stream_t stream) {
+  ISB_CHECK_ARG(ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "isb_prefetch_l2: pointer must be 16-byte aligned");
+  if (bytes < 16) return ISB_OK;
+  const size_t chunks = (bytes + isb::PF_CHUNK - 1) / isb::PF_CHUNK;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>((chunks + 127) / 128));
+  cfg.blockDim = dim3(128);
+  cfg.stream = isb::as_stream(stream);
+  ISB_CUDA(cudaLaunchKernelEx(&cfg, isb::prefetch_l2_kernel, static_cast<const char*>(ptr), bytes));
+  isb::g_launches.fetch_add(1);
+  ISB_LAUNCH_CHECK();
+  return ISB_OK;
+}
 
 int isb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int H, int W, int c_pad,
                      isb_stream_t stream) {

@@ -265,6 +265,16 @@ class GuidedStepper:
             self._ev_fork, self._ev_join = th.cuda.Event(), th.cuda.Event()
             self._side_bwd = (th.cuda.Stream(device=dev, priority=hi), th.cuda.Event(), th.cuda.Event())
         self._film = {}
+        # background L2 prefetch of the next layers' weight panels inside the captured step (ops.weight_prefetch).
+        # MEASURED AND OFF: 4.90 ms with it, 4.77 ms without (tools/ab_step.py on B200).  The conv launches take the same
+        # time with L2-warm and HBM-cold weights (profiles/r01_conv_auto_{warm,cold}_weights.txt: 15.4 vs 15.7 us for the
+        # 8x8 1024->1024 layer): PDL already streams the first weight tiles under the predecessor's tail, and the
+        # mainloop is bound by the producer thread's per-iteration latency, not by HBM.  The ~200 extra graph nodes and
+        # cross-stream edges only add launch overhead.  Kept behind ISB_WEIGHT_PREFETCH=1 with its test.
+        self._prefetch = os.environ.get("ISB_WEIGHT_PREFETCH", "0") == "1" and dev.type == "cuda"
+        self._pf_window = int(float(os.environ.get("ISB_PREFETCH_WINDOW_MB", "48")) * (1 << 20))
+        self._pf_seq = None
+        self._pf_stream = th.cuda.Stream(device=dev, priority=0) if dev.type == "cuda" else None
         self._film_cache = os.environ.get("ISB_FILM_CACHE", "1") != "0"
         self._bwd_branches = os.environ.get("ISB_SIDE_BWD", "1") != "0"
         self._graph = None
@@ -352,12 +362,21 @@ class GuidedStepper:
         if self._graph is None:
             if self._warm < 1:          # eager warm-up sizes every workspace/scratch buffer
                 self._warm += 1
-                self._body()
+                if self._prefetch:      # ... and records the order in which the weight panels are touched
+                    with self.ops.record_weight_sequence() as seq:
+                        self._body()
+                    self._pf_seq = list(seq)
+                else:
+                    self._body()
                 return
             img_keep = self.img.clone()
             g = th.cuda.CUDAGraph()
             with th.cuda.graph(g, stream=self._cap_stream):
-                self._body()
+                if self._prefetch and self._pf_seq:
+                    with self.ops.weight_prefetch(self._pf_seq, self._pf_stream, self._pf_window):
+                        self._body()
+                else:
+                    self._body()
             self._graph = g
             self.img.copy_(img_keep)    # capture does not execute; restore and replay for real
         self._graph.replay()

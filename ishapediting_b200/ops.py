@@ -67,6 +67,8 @@ class CudaOps:
         # counters must stay 0 between launches, so they are never returned to the caching allocator.
         self._retired = []
         self._mlp_bounds = {}
+        self._pf_rec = None          # weight-prefetch recording: [(ptr, bytes)] of the conv launches of one pass
+        self._pf = None              # active prefetch schedule (inside weight_prefetch())
 
     # ---- memory -----------------------------------------------------------
     def empty(self, shape, dtype=torch.float32):
@@ -112,6 +114,63 @@ class CudaOps:
             yield
         finally:
             self._bg = prev
+
+    # ---- background L2 prefetch of the weight panels ------------------------------------------------
+    # At batch 1 every launch of the step is latency-bound and HBM sits idle ~95 % of the time, while each conv starts by
+    # pulling COLD weights (1.57 GB per step against 126 MB of L2) through a 3-4 stage ring: the small-spatial layers run
+    # at ~10 % of their weight-streaming roofline (profiles/r02_ncu_step_traffic.md).  Inside a captured step the launch
+    # sequence is static, so a side stream can pull the panels of the next layers into L2 while the current ones run.
+    @contextlib.contextmanager
+    def record_weight_sequence(self):
+        """Record (pointer, bytes) of every conv weight panel launched inside the context, in issue order."""
+        self._pf_rec = []
+        try:
+            yield self._pf_rec
+        finally:
+            self._pf_rec = None
+
+    @contextlib.contextmanager
+    def weight_prefetch(self, seq, stream, window_bytes=48 << 20, min_bytes=1 << 20):
+        """Inside the context (a graph capture of the pass that produced `seq`) the k-th conv launch first gates the L2
+        prefetch of the panels of the following launches — as many as fit `window_bytes` — on its own start, on
+        `stream`.  The caller's stream joins `stream` when the context ends."""
+        st = self._pf = {"seq": seq, "k": 0, "upto": 0, "ahead": 0, "stream": stream, "window": window_bytes,
+                         "min": min_bytes, "used": False}
+        try:
+            yield
+        finally:
+            self._pf = None
+            if st["used"]:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                torch.cuda.current_stream().wait_event(ev)
+
+    def _pf_step(self, ptr):
+        st = self._pf
+        seq, k = st["seq"], st["k"]
+        st["k"] = k + 1
+        if k >= len(seq) or seq[k][0] != ptr:        # the pass diverged from the recording: stop prefetching
+            st["k"] = len(seq) + 1
+            return
+        if st["upto"] <= k:                           # this launch was not prefetched (first launches, window jumps)
+            st["upto"], st["ahead"] = k + 1, 0
+        else:
+            st["ahead"] -= seq[k][1]
+        todo = []
+        while st["upto"] < len(seq) and (st["ahead"] + seq[st["upto"]][1] <= st["window"] or st["upto"] == k + 1):
+            j = st["upto"]
+            st["upto"] += 1
+            st["ahead"] += seq[j][1]
+            if seq[j][1] >= st["min"]:
+                todo.append(seq[j])
+        if todo:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())    # = "launch k is about to start"
+            st["stream"].wait_event(ev)
+            sp = C.c_void_p(st["stream"].cuda_stream)
+            for ptr_j, nbytes in todo:
+                _lib.check(self.lib.isb_prefetch_l2(C.c_void_p(ptr_j), nbytes, sp), "isb_prefetch_l2")
+            st["used"] = True
 
     def _scratch(self, N, groups=32, which="fwd"):
         """GroupNorm reduction scratch (arrival counters + partials).  Forward and backward kernels get
@@ -233,6 +292,10 @@ class CudaOps:
         if tune and tune.get("trace") is not None:      # profiling: debug bit 2 -> phase stamps land in this tensor
             self.lib.isb_debug_set_trace(_p(tune["trace"]))
         ws, ws_bytes = self._workspace(self.lib.isb_conv2d_workspace(C.byref(d)))
+        if self._pf_rec is not None:
+            self._pf_rec.append((w.data_ptr(), w.numel() * w.element_size()))
+        if self._pf is not None:
+            self._pf_step(w.data_ptr())
         _lib.check(self.lib.isb_conv2d(C.byref(d), _p(ws), ws_bytes, _stream()), "isb_conv2d")
         return out
 
