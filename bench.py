@@ -125,13 +125,11 @@ def reference_training_steps(device, n_steps, n_warm, budget_s=150.0, fp16=False
         torch.set_num_threads(threads)
     torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
     torch.backends.cudnn.allow_tf32 = bool(tf32)
-    if not dist.is_initialized():      # the reference's setup_dist() would resolve the container hostname
-        import socket
-        s = socket.socket()
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
-        s.close()
-        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    if not dist.is_initialized():
+        # The reference's setup_dist() would resolve the container hostname and rendezvous over TCP; under torchrun a
+        # tcp:// rendezvous is redirected to the elastic agent's store (TORCHELASTIC_USE_AGENT_STORE) and never
+        # completes for a private single-rank group.  An in-process HashStore needs no network at all.
+        dist.init_process_group("gloo", store=dist.HashStore(), rank=0, world_size=1)
     ns = R.import_reference()
     du = ns.drag_utils
     if du is None:
@@ -250,6 +248,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every worker; the reference arm is ONE process that owns all host cores.
+    # Must happen before torch is imported (OpenMP / MKL read it at load time).
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(os.cpu_count() or 1)
     r = cpu_reference_steps(args.steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": r["done"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
