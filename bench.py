@@ -489,6 +489,24 @@ def run_ours(args):
                    "what": f"{Bn} independent edits per GPU advanced as one batch-{Bn} guided step"}
         del stb, origin_b
         torch.cuda.empty_cache()
+        # the same as whole edits through the product API: Bn x (50 steps + 256^3 decode) per GPU, latents gathered
+        edits_b = [_problem(5000 + rank * 64 + b) for b in range(Bn)]
+        ds.training_batch(edits_b, scale=600, cof=0.2)                      # warm-up: captures the batch-Bn graph
+        edits_b = [_problem(6000 + rank * 64 + b) for b in range(Bn)]
+
+        def batch_edits():
+            lat_b, vols = ds.training_batch(edits_b, scale=600, cof=0.2)
+            return parallel.gather_results(lat_b, Bn * world)
+
+        ms_be, all_b = timed(batch_edits)
+        ms_be = max_over_ranks([ms_be])[0]
+        batched.update(edits_per_s=world * Bn / (ms_be / 1e3), ms_per_batch_of_edits=ms_be,
+                       edits_what=f"BASELINE configs[4], batched variant: {Bn} whole edits per GPU ({W_TIME} batch-{Bn} steps + "
+                                  f"{Bn} x {DECODE_RES}^3 decodes) via DragStuff.training_batch, latents all-gathered",
+                       gathered_ok=bool(all_b.shape[0] == Bn * world and torch.isfinite(all_b).all()))
+        del all_b
+        ds.batch_stepper = None
+        torch.cuda.empty_cache()
 
     # ---- rooflines (rank 0): ablation of one kernel family out of the graph-replayed step ----
     roof = roof_gn = roof_dec = None

@@ -288,13 +288,13 @@ class GuidedStepper:
         return (self.weights_generation == self.model.weights_generation and geometry.npts == self.geo.npts and geometry.group_size == self.geo.group_size
                 and float(cof) == self.cof and (1 if loss_type == "l1" else 0) == self.loss_type)
 
-    def retarget(self, geometry, scale):
-        """Load a new edit's geometry into the static device buffers (no re-capture)."""
-        g = geometry
+    def retarget(self, geometry, scale, b=0):
+        """Load a new edit's geometry into the static device buffers of batch slot b (no re-capture)."""
+        g, geo = geometry, self.geos[b]
         for k in ("patch_xy", "shift_xy", "weight", "bbox", "mask"):
-            getattr(self.geo, k).copy_(getattr(g, k))
-        self.geo.mask_count, self.geo.inv_count = g.mask_count, g.inv_count
-        self.dyn.copy_(th.tensor([g.inv_count, 1.0 / (max(g.mask_count, 1) * self.Ca)], dtype=th.float32))
+            getattr(geo, k).copy_(getattr(g, k))
+        geo.mask_count, geo.inv_count = g.mask_count, g.inv_count
+        self.dyns[b].copy_(th.tensor([g.inv_count, 1.0 / (max(g.mask_count, 1) * self.Ca)], dtype=th.float32))
         if float(scale) != self.scale:
             self.scale = float(scale)
             self.coef_table = self.diffusion.coef_table(self.ops.device, guide_scale=self.scale)
@@ -787,6 +787,34 @@ class DragStuff:
                 self.track_error = (self.tracked - self.targets).abs().amax(dim=1) / self.voxel_size
             yield 1 - i / (w_time - 1.) if w_time > 1 else 1.0
         self.mesh = self.get_mesh(img=stepper.img.clone(), t=stop_time)
+
+    def training_batch(self, edits, scale=600, cof=0.2, noises=None, decode=True):
+        """Throughput mode (BASELINE configs[4], "batched" variant of SURVEY.md §8d config 5): B independent drags of
+        the CURRENT shape — `edits` = [(sources, targets), ...] with the same number of handles — advanced together as
+        one batch-B guided step per timestep (the reference handles one edit at a time, :303-304; each edit here is
+        exactly its own `training()` run: same start latent self.w, same cached origin features, its own handles).
+        Returns (latents (B,96,R,R), [volume or mesh per edit] if `decode`)."""
+        S, Ca = self.feature_guidance[0].shape[1], self.feature_guidance[0].shape[3]
+        geos = [DragGeometry(np.asarray(s_), np.asarray(t_), self.r1, self.voxel_size, S, Ca) for s_, t_ in edits]
+        B = len(geos)
+        st = getattr(self, "batch_stepper", None)
+        reuse = (st is not None and st.batch == B and st.weights_generation == self.model.weights_generation
+                 and all(st.compatible(g, cof, self.args.loss_type) for g in geos))
+        if reuse:
+            for b, g in enumerate(geos):
+                st.retarget(g, scale, b)
+        else:
+            st = GuidedStepper(self.model, self.diffusion, geos, self.args.feat_layer, cof, self.args.loss_type, scale,
+                               clip_denoised=True, use_graph=self.use_graph)
+        self.batch_stepper = st
+        st.img.copy_(self.w.detach().expand(B, -1, -1, -1))
+        w_time = self.args.w_time
+        for i in range(w_time - 1, -1, -1):
+            st.step(i, self.feature_guidance[w_time - 1 - i], None if noises is None else noises[w_time - 1 - i])
+        lat = st.img.clone()
+        if not decode:
+            return lat, None
+        return lat, [self.get_mesh(tri_feat=lat[b:b + 1]) for b in range(B)]
 
     # ---- real-shape inversion (reference :552-566) -----------------------------------------------------------
     def latent_inversion(self, tri_feat):

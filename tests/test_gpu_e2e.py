@@ -176,3 +176,37 @@ def test_train_triplane_flow_runs():
     assert img.shape == (1, 96, 32, 32) and torch.isfinite(img).all()
     vol = ds.mesh if torch.is_tensor(ds.mesh) else ds.last_volume
     assert vol.numel() == 32 ** 3 and torch.isfinite(vol).all()
+
+
+def test_training_batch_matches_sequential_edits():
+    """DragStuff.training_batch (B drags of one shape as one batch-B step per timestep) against B separate training()
+    runs with the same noise: identical edits, only the kernel tiling differs with the batch size."""
+    from ishapediting_b200.drag_utils import DragStuff, get_args
+
+    cfg = _cfg()
+    sd = O.synth_state_dict(cfg)
+    a = get_args(["--num_steps", "20", "--w_time", "4", "--shape_resolution", "32", "--feat_layer", "5", "--resolution", "32"])
+    a.channel_mult, a.attention_resolutions, a.use_fp16 = "1,2,4", "16,8", True
+    ds = DragStuff(args=a, device=DEV, use_graph=True)
+    ds.mesh_on_device = False
+    ds.model.load_state_dict(sd)
+    ds.model.to(DEV).eval()
+    ds.set_offset1(4)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 96, 32, 32, generator=g).to(DEV)
+    noise = torch.randn(1, 96, 32, 32, generator=g).to(DEV)
+    ds.update_latent_params(x, noise=noise)
+    edits = []
+    for b in range(3):
+        src = (torch.rand(3, 3, generator=g) - 0.5).numpy()
+        edits.append((src, src + (torch.rand(3, 3, generator=g).numpy() - 0.5) * 0.4))
+    seq = []
+    for src, tgt in edits:
+        list(ds.training(src, tgt, scale=600, cof=0.2, noises=[noise] * 4))
+        seq.append((ds.stepper.img.clone(), ds.last_volume.clone()))
+    for rep in range(2):                                   # second call reuses the captured batch graph (retarget)
+        lat, vols = ds.training_batch(edits if rep == 0 else edits[::-1], scale=600, cof=0.2, noises=[noise.expand(3, -1, -1, -1)] * 4)
+        order = range(3) if rep == 0 else range(2, -1, -1)
+        for b, e in enumerate(order):
+            assert rel_l2(lat[b:b + 1], seq[e][0]) < 5e-3, (rep, b)
+            assert vols[b].shape == seq[e][1].shape
