@@ -420,10 +420,15 @@ fa_bwd_kernel(const FaParams p) {
 constexpr int FA_SMEM_FWD = 5 * FA_TILE;   // 46080
 constexpr int FA_SMEM_BWD = 6 * FA_TILE;   // 55296
 
+// attention_tc.cu: the forward on tcgen05 / TMEM / TMA for T % 128 == 0
+int attention_tc_init();
+bool attention_tc_usable(int T, int ch);
+int attention_tc_forward(const void* qkv, int N, int T, int heads, void* out, float* lse, float scale_log2, cudaStream_t st);
+
 int attention_flash_init() {
   ISB_CUDA(cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FWD));
   ISB_CUDA(cudaFuncSetAttribute(fa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BWD));
-  return ISB_OK;
+  return attention_tc_init();
 }
 
 static int fa_check(const char* who, int N, int T, int heads, int ch) {
@@ -450,6 +455,8 @@ int isb_attention_flash_forward(const void* qkv, int N, int T, int heads, int ch
   p.heads = heads;
   p.scale = 1.0f / sqrtf(static_cast<float>(ch));
   p.scale_log2 = p.scale * 1.4426950408889634f;
+  if (isb::attention_tc_usable(T, ch))      // T % 128 == 0: the tcgen05 / TMEM / TMA kernel (attention_tc.cu)
+    return isb::attention_tc_forward(qkv, N, T, heads, out, lse, p.scale_log2, isb::as_stream(stream));
   isb::PdlFamily fam(3);
   ISB_CUDA(isb::launch(isb::fa_fwd_kernel, dim3(T / isb::FA_B, heads, N), dim3(128), isb::FA_SMEM_FWD,
                        isb::as_stream(stream), p));

@@ -274,3 +274,36 @@ def test_edit_end_to_end_iou(mode, min_iou):
         print("edit end-to-end bf16: flipped voxels", int(wrong.sum()), "rms dlogit", bound / 6.0,
               "flipped with |logit_ref| > 6 sigma:", far)
         assert far <= 0.01 * float(wrong.sum())       # the logit perturbation is heavy-tailed: 51 of 12 647 measured
+
+
+@pytest.mark.parametrize("npts", [0, 1, 127, 128, 129, 1000])
+def test_decoder_ragged_point_counts(npts):
+    """The tcgen05 decoder works on 128-point tiles: empty, single-point and ragged inputs must match the oracle."""
+    dec, w, planes = build_decoder(128, DEV)
+    for p in range(3):
+        dec.embeddings[p] = planes[[p]].to(DEV)
+    g = torch.Generator().manual_seed(npts + 3)
+    pts = torch.rand(npts, 3, generator=g) * 2.2 - 1.1           # some outside [-1,1]: zeros padding
+    out = dec(0, pts[None].to(DEV)).reshape(-1).cpu()
+    assert out.shape == (npts,)
+    if npts:
+        ref = O.triplane_forward(w, planes, pts)
+        assert float((out - ref).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("res", [48, 130, 384])
+def test_decoder_grid_paths_agree_with_point_queries(res):
+    """Dense-grid decode at resolutions that take the per-point sampling path (res % 128 != 0) and the cooperative row
+    path (res % 128 == 0): both must equal the arbitrary-points kernel on the same coordinates, slab by slab."""
+    from ishapediting_b200.triplane_decoder.visualize import query_volume
+
+    dec, w, planes = build_decoder(128, DEV)
+    for p in range(3):
+        dec.embeddings[p] = planes[[p]].to(DEV)
+    xb, xe = res // 3, res // 3 + 2                              # two x-slabs in the middle of the grid
+    vol = query_volume(dec, 0, res=res, x_begin=xb, x_end=xe).reshape(-1)
+    coords = O.dense_grid_coords(res, xb, xe)
+    pts = dec(0, coords[None].to(DEV)).reshape(-1)
+    assert float((vol - pts).abs().max()) < 2e-6
+    ref = O.triplane_forward(w, planes, coords[:20000])
+    assert float((vol[:20000].cpu() - ref).abs().max()) < 1e-4

@@ -103,3 +103,34 @@ def test_track_finds_a_planted_feature():
     side = 2 * r + 1
     assert int(idx) == ((dx + r) * side + (dy + r)) * side + (dz + r)
     assert float(dist) < 1e-3 * float(f0.abs().sum())
+
+
+def test_training_with_tracking_runs_and_reports_lattice_points():
+    """DragStuff.training(track=True): the guided update is unchanged (same latents as track=False), the tracked
+    handles stay on the voxel lattice around their previous position, and track_error is reported in voxels."""
+    from oracle import nfd_oracle as O
+    from ishapediting_b200.drag_utils import DragStuff, get_args
+
+    cfg = O.mid_cfg()
+    cfg.update(in_out_channels=96, timestep_respacing="20")
+    a = get_args(["--num_steps", "20", "--w_time", "3", "--shape_resolution", "16", "--feat_layer", "5", "--resolution", "32"])
+    a.channel_mult, a.attention_resolutions, a.use_fp16 = "1,2,4", "16,8", True
+    ds = DragStuff(args=a, device=DEV, use_graph=True)
+    ds.mesh_on_device = False
+    ds.model.load_state_dict(O.synth_state_dict(cfg))
+    ds.model.to(DEV).eval()
+    ds.set_offset1(3)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 96, 32, 32, generator=g).to(DEV)
+    noise = torch.randn(1, 96, 32, 32, generator=g).to(DEV)
+    ds.update_latent_params(x, noise=noise)
+    src = (torch.rand(2, 3, generator=g) - 0.5).numpy()
+    tgt = src + 0.05
+    list(ds.training(src, tgt, scale=600, cof=0.2, noises=[noise] * 3))
+    plain = ds.stepper.img.clone()
+    list(ds.training(src, tgt, scale=600, cof=0.2, noises=[noise] * 3, track=True, track_radius=3))
+    assert torch.equal(ds.stepper.img, plain)                       # tracking only observes
+    assert ds.tracked.shape == (2, 3) and ds.track_error.shape == (2,)
+    steps = (ds.tracked.cpu() - torch.from_numpy(src)) / ds.voxel_size
+    assert float((steps - steps.round()).abs().max()) < 1e-3         # on the lattice
+    assert float(steps.abs().max()) <= 3 * 3 + 1e-3                  # at most r voxels per step, 3 steps
