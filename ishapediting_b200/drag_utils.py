@@ -117,7 +117,8 @@ def resize_feat_align(feature, cat_var=True):
 def handle_features(origin_feature, points):
     """f0 [B,3,Ca]: the aligned triplane feature of each 3-D point (bilinear, align_corners=True, zeros — the sampling
     of reference :355-358) taken from a cached origin feature (3,S,S,Ca channels-last, a feature_guidance entry)."""
-    pts = th.as_tensor(np.asarray(points), dtype=th.float32, device=origin_feature.device).reshape(-1, 3)
+    pts = points if th.is_tensor(points) else th.as_tensor(np.asarray(points))
+    pts = pts.to(device=origin_feature.device, dtype=th.float32).reshape(-1, 3)
     planes = origin_feature.permute(0, 3, 1, 2)                                   # (3, Ca, S, S) view
     axes = ((0, 1), (1, 2), (0, 2))
     grid = th.stack([pts[:, list(a)] for a in axes], dim=0).unsqueeze(2)          # (3, B, 1, 2): (u -> W, v -> H)

@@ -544,6 +544,8 @@ class CudaOps:
 
     def decode_points_backward(self, planes_hwc, weights, coords, d_logits, d_planes_hwc):
         """d_planes_hwc (3,R,R,32) += d(sum_i d_logits[i] * logit_i) / d planes   (zero-fill it first)."""
+        if coords.shape[0] == 0:
+            return d_planes_hwc
         for t in (planes_hwc, coords, d_logits, d_planes_hwc):
             _chk(t, torch.float32)
         assert d_planes_hwc.shape == planes_hwc.shape and d_logits.numel() == coords.shape[0]
@@ -555,6 +557,8 @@ class CudaOps:
         return d_planes_hwc
 
     def decode_points(self, planes_hwc, weights, coords, out):
+        if coords.shape[0] == 0:
+            return out
         _chk(planes_hwc, torch.float32); _chk(coords, torch.float32); _chk(out, torch.float32)
         m = self._mlp(weights)
         _lib.check(self.lib.isb_triplane_decode_points(_p(planes_hwc), planes_hwc.shape[1], C.byref(m), _p(coords),
