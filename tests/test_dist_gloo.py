@@ -21,6 +21,7 @@ def _free_port():
 
 def _worker(rank, world, port, res, n_edits, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")       # the container hostname may not resolve
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from ishapediting_b200.parallel import (assign_edits, decode_volume_sharded, gather_results, gather_volume,
                                             slab_range)
@@ -44,26 +45,42 @@ def _worker(rank, world, port, res, n_edits, q):
     local = torch.tensor([[float(k), float(k * k)] for k in mine])
     allr = gather_results(local, n_edits)
     if rank == 0:
-        q.put((vol, vol2, allr))
+        q.put((vol.numpy(), vol2.numpy(), allr.numpy()))      # by value: no shared-memory handles that die with the rank
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _run_world(res, n_edits, world=2, attempts=3):
+    """Spawn `world` gloo ranks; a rendezvous that loses the race for its port is retried on a fresh one."""
+    ctx = mp.get_context("spawn")
+    last = None
+    for _ in range(attempts):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, res, n_edits, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        try:
+            got = q.get(timeout=170)
+        except Exception:  # noqa: BLE001 - queue.Empty: the rendezvous did not come up
+            got = None
+        for p in procs:
+            p.join(30)
+        codes = [p.exitcode for p in procs]
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+        if got is not None and all(c == 0 for c in codes):
+            return tuple(torch.from_numpy(a) for a in got)
+        last = codes
+    raise AssertionError(f"gloo world-{world} run failed {attempts} times, exit codes {last}")
 
 
 @pytest.mark.parametrize("res,n_edits", [(13, 5), (12, 6)])
 def test_slab_sharded_decode_and_edit_gather_world2(res, n_edits):
     """res=13: ragged slabs (7 + 6 rows, one broadcast per rank); res=12: equal slabs, ONE in-place
     all_gather_into_tensor whose send buffer is this rank's slice of the receive buffer."""
-    world = 2
-    ctx = mp.get_context("spawn")
-    q = ctx.SimpleQueue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, res, n_edits, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    vol, vol2, allr = q.get()
-    for p in procs:
-        p.join(120)
-        assert p.exitcode == 0
+    vol, vol2, allr = _run_world(res, n_edits)
     w, planes = O.synth_decoder(R=32)
     ref = O.decode_grid(w, planes, res).view(res, res, res)
     assert vol.shape == ref.shape
