@@ -14,6 +14,7 @@
 // warps 2..5 = epilogue (TMEM lanes 32*(warp%4) ..).  Split-K partials go to a
 // caller workspace; the last CTA to arrive for an output tile reduces them in fixed order
 // (deterministic) and runs the epilogue — no separate reduction launch.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace isb {
@@ -36,6 +37,7 @@ struct TcParams {
   int k_iters, splits, stages;
   int w_tiled;     // 1: weights packed as [Cout/64][K/64][64][64] panels (8 KiB contiguous per TMA box row-group)
   int debug;       // profiling only: bit0 = producer skips the TMA loads, bit1 = MMA thread skips the MMAs
+  int a_bytes;     // bytes of the A tile actually loaded per stage (= 16 KiB, or less when the image has < 128 pixels)
   int two_cta;     // 1: CTA pair (cta_group::2): 256-row MMA, each CTA stages its A half and half of the B tile
   int cluster;     // 1: the `splits` CTAs of an output tile form a thread-block cluster (DSMEM reduce)
   int tmem_cols;
@@ -586,7 +588,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
-  const uint32_t stage_bytes = TC_A_STAGE + static_cast<uint32_t>(p.block_n) * 128u;
+  // Images with fewer than 128 pixels (8x8): only the valid rows of the A tile are loaded and a stage shrinks to them,
+  // so the ring holds more WEIGHT bytes (what these layers stream).  The MMA still reads 128 rows — the rows past the
+  // loaded ones alias the stage's weight tile: garbage that lands in accumulator rows the epilogue never stores.
+  const uint32_t a_stage = static_cast<uint32_t>(p.a_bytes);
+  const uint32_t stage_bytes = a_stage + static_cast<uint32_t>(p.block_n) * 128u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -656,7 +662,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int i = 0; i < npre; ++i) {
         mbar_expect_tx(full0 + 8u * i, skip_tma ? 0u : stage_bytes);
         if (!skip_tma) {
-          const uint32_t b_dst = tiles_addr + static_cast<uint32_t>(i) * stage_bytes + TC_A_STAGE;
+          const uint32_t b_dst = tiles_addr + static_cast<uint32_t>(i) * stage_bytes + a_stage;
           if (p.w_tiled) tma_load_4d(b_dst, &mapB, full0 + 8u * i, 0, 0, k_begin + i, cout0 / 64);
           else tma_load_2d(b_dst, &mapB, full0 + 8u * i, (k_begin + i) * TC_BLOCK_K, cout0);
         }
@@ -704,8 +710,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_expect_tx(fb, skip_tma ? 0u : stage_bytes);
         if (!skip_tma) {
           load_a(a_dst, fb);
-          if (p.w_tiled) tma_load_4d(a_dst + TC_A_STAGE, &mapB, fb, 0, 0, k_begin + i, cout0 / 64);
-          else tma_load_2d(a_dst + TC_A_STAGE, &mapB, fb, (k_begin + i) * TC_BLOCK_K, cout0);
+          if (p.w_tiled) tma_load_4d(a_dst + a_stage, &mapB, fb, 0, 0, k_begin + i, cout0 / 64);
+          else tma_load_2d(a_dst + a_stage, &mapB, fb, (k_begin + i) * TC_BLOCK_K, cout0);
         }
         tc_stamp_iter(p.trace, i, 1);
         if (++s == p.stages) {
@@ -728,7 +734,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t ph = 0;
       uint64_t adesc = make_desc_sw128(tiles_addr);
       const uint64_t desc_step = static_cast<uint64_t>(stage_bytes >> 4);
-      const uint64_t desc_b_off = static_cast<uint64_t>(TC_A_STAGE >> 4);
+      const uint64_t desc_b_off = static_cast<uint64_t>(a_stage >> 4);
       const uint64_t adesc0 = adesc;
       for (int i = 0; i < niter; ++i) {
         mbar_wait(full0 + 8u * s, ph);
@@ -869,7 +875,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const float* tile_base = p.partial + tile_id * p.splits * static_cast<size_t>(TC_BLOCK_M) * p.block_n;
       if (p.splits == 2) cluster_fold<2>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0, gn_slot(p, tile_w, tile_h, split));
       else if (p.splits == 4) cluster_fold<4>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0, gn_slot(p, tile_w, tile_h, split));
-      else cluster_fold<8>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0, gn_slot(p, tile_w, tile_h, split));
+      else if (p.splits == 8) cluster_fold<8>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0, gn_slot(p, tile_w, tile_h, split));
+      else cluster_fold<16>(p, out_dst, tile_base, split, et, n0, h0, w0, cout0, gn_slot(p, tile_w, tile_h, split));
     }
     if (threadIdx.x == 64) tc_stamp(p.trace, 8);
   }
@@ -1089,6 +1096,7 @@ void conv_tc_set_trace(void* ptr) { g_trace = ptr; }
 
 struct TcPlan {
   TcParams p;
+  int a_nb;         // images per A-tile TMA box (p.nb, or fewer when only valid rows are loaded)
   int gn_slots;     // contributions per (image, group) this launch writes when gn statistics are fused (0: unsupported)
   int smem_bytes;
   size_t ws_bytes;
@@ -1168,7 +1176,8 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   int splits = d->split_k ? d->split_k : splits_for(tiles);
   ISB_CHECK_ARG(splits >= 1 && splits <= p.k_iters, "conv_tc: split_k=%d out of range (k_iters=%d)", splits, p.k_iters);
   p.splits = splits;
-  p.cluster = (splits == 2 || splits == 4 || splits == 8) ? 1 : 0;   // other counts: workspace fold
+  p.cluster = (splits == 2 || splits == 4 || splits == 8 || splits == 16) ? 1 : 0;   // other counts: workspace fold
+  // (16 CTAs per cluster is beyond the portable limit: conv_tc_init() opts in, cudaFuncAttributeNonPortableClusterSizeAllowed)
   // CTA pairs for the big, un-split layers: 256-wide N tile, both m-tiles of a pair share the weight tile
   int two = d->two_cta;
   if (two == 0 && d->block_n == 0 && splits == 1 && mtiles % 2 == 0 && mtiles >= 64 && d->Cout % 128 == 0 && !d->w_tiled) {
@@ -1188,12 +1197,29 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
     ntiles = cdiv(d->Cout, bn);
     tiles = mtiles * ntiles;
   }
-  const int stage_bytes = TC_A_STAGE + (p.two_cta ? bn / 2 : bn) * 128;
+  // A tile bytes per stage: the whole 128-row tile, or only the valid rows when ALL tiles are partial (N*H*W < 128)
+  p.a_bytes = TC_A_STAGE;
+  int a_nb = p.nb;
+  static const bool compact_a = [] {
+    const char* e = getenv("ISB_COMPACT_A");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  if (compact_a && !p.two_cta && p.tiles_n == 1 && d->N < p.nb && bn >= 64 && !d->w_tiled) {
+    a_nb = d->N;
+    p.a_bytes = a_nb * p.tw * p.th * 128;
+  }
+  plan->a_nb = a_nb;
+  const int stage_bytes = p.a_bytes + (p.two_cta ? bn / 2 : bn) * 128;
   const int max_stages = (TC_SMEM_LIMIT - 1024) / stage_bytes;
   int stages = d->stages;
   if (stages == 0) {
     if (p.two_cta) {
       stages = bn <= 128 ? 4 : 5;
+    } else if (p.a_bytes < TC_A_STAGE) {
+      stages = (96 * 1024) / stage_bytes;            // same 96 KB budget (PDL co-residency), more slots
+      if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+      const int per_cta = cdiv(p.k_iters, splits);
+      if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
     } else {
       stages = bn <= 64 ? 4 : bn <= 128 ? 3 : 4;    // <= 96 KB (see above); 256-wide tiles cannot, they get 4
       const int per_cta = cdiv(p.k_iters, splits);
@@ -1302,6 +1328,7 @@ static int encode_weight_map_tiled(CUtensorMap* m, const void* ptr, int Cout, in
 int conv_tc_init() {
   ISB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
   ISB_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+  ISB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   return ISB_OK;
 }
 
@@ -1343,10 +1370,10 @@ int conv_tc_launch(const isb_conv_desc* d, void* ws, size_t ws_bytes, cudaStream
   }
   if (p.debug & 4) p.trace = static_cast<unsigned long long*>(g_trace);   // profiling: isb_debug_set_trace()
   CUtensorMap mapA, mapA2, mapB;
-  rc = encode_act_map(&mapA, d->a, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.nb);
+  rc = encode_act_map(&mapA, d->a, d->N, d->H, d->W, d->Cin, p.tw, p.th, plan.a_nb);
   if (rc) return rc;
   if (d->a2) {
-    rc = encode_act_map(&mapA2, d->a2, d->N, d->H, d->W, d->Cin2, p.tw, p.th, p.nb);
+    rc = encode_act_map(&mapA2, d->a2, d->N, d->H, d->W, d->Cin2, p.tw, p.th, plan.a_nb);
     if (rc) return rc;
   } else {
     mapA2 = mapA;
