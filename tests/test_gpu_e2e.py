@@ -19,7 +19,9 @@ def _cfg():
     return c
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("bf16", 5e-2)])
+# Tolerances = BASELINE.json's (fp32 mode 1e-4, bf16 mode 2e-2 relative L2).  Measured on B200 over the whole flow (20 no-grad
+# steps, 4 guided steps): fp32 6e-7 .. 1.9e-6, bf16 1.5e-3 (w) .. 5.7e-3 (first cached feature).
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
 def test_dragstuff_edit_flow(mode, tol):
     from ishapediting_b200.drag_utils import DragStuff, get_args
 
@@ -117,11 +119,14 @@ def test_latent_inversion_flow_fp32():
     assert float((img - x0.cpu()).abs().max()) < 5e-4
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-3), ("bf16", 3e-2)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 5e-4), ("bf16", 2e-2)])
 def test_recon_guided_step(mode, tol):
     """One iteration of the reference's reconstruction guidance (train_triplane, drag_utils.py:445-463) on the GPU:
-    UNet forward + FULL input-gradient backward on the kernel plan, decoder forward / backward kernels.  The fp32
-    tolerance reflects the conditioning of the decoder gradient (tests/test_host_logic.py), not kernel error."""
+    UNet forward + FULL input-gradient backward on the kernel plan, decoder forward / backward kernels.
+    Measured on B200: next latent 6.5e-5 (fp32 mode) / 4.2e-3 (bf16 mode).  The fp32 figure is above the 1e-4 of the
+    drag path because the guidance differentiates THROUGH sin / cos of arguments of hundreds of radians: the decoder
+    gradient amplifies fp32 rounding of the sampled features ~1e3-fold (shown on the CPU, float32 vs float64 of the
+    reference formula, in tests/test_host_logic.py) — the bound asserted is 8x the measurement, not a kernel tolerance."""
     from ishapediting_b200.drag_utils import recon_guided_step
     from tests.helpers import build_decoder, build_model, recon_inputs
 
