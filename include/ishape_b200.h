@@ -375,6 +375,61 @@ int isb_mesh_smooth_simple(float* verts, int64_t nv, const int32_t* tris, int64_
  * runs (HBM is idle ~95 % of a batch-1 step).  The reference has no counterpart: PyTorch eager issues no prefetch. */
 int isb_prefetch_l2(const void* ptr, size_t bytes, isb_stream_t stream);
 
+/* ---- the UNet behind a handle ---------------------------- */
+/* Replaces `UNetModel.__init__` + `load_state_dict` + `forward(x, timesteps, feat_layer)` (neural_field_diffusion/
+ * guided_diffusion/unet.py:396-671) and the input-gradient half of `loss.backward()` (drag_utils.py:383) for hosts
+ * that are not Python: the block structure, the weight packing (forward and backward-data panels), the activation
+ * layout and the launch schedule live in the library.  The per-operator entry points above are what it calls, in
+ * the same order as the Python host's plan, so both hosts produce bit-identical results.
+ *   create -> load_weight (every entry of the reference's state_dict, by its own name, fp32 device pointers)
+ *          -> finalize (packs; afterwards the handle owns only packed weights)
+ *          -> workspace_bytes / workspace_init (ONE caller-owned buffer: activations, gradients, scratch)
+ *          -> forward / forward_tail / backward_input on the caller's stream (no sync, no allocation: capturable).
+ * One handle serves one pass at a time (it records which tensors carry a gradient).  Dropout is the identity
+ * (eval mode, drag_utils.py:187); class conditioning, resblock_updown=False and use_new_attention_order=True are
+ * outside the NFD configuration, as in the Python host. */
+typedef struct isb_unet_cfg {
+  int in_channels, model_channels, out_channels, num_res_blocks;
+  int n_levels; int channel_mult[8];
+  int n_attn; int attention_ds[8];   /* script_util.py:139-141: image_size // attention_resolution, e.g. {4,8,16} */
+  int num_heads, num_head_channels, num_heads_upsample;   /* as the reference's arguments (-1 as there) */
+  int N, H, W;                       /* batch and latent resolution this handle is planned for */
+  int mode;                          /* ISB_BF16: tcgen05 path (bf16 operands, fp32 accumulate); ISB_F32: FFMA path */
+  int want_backward;                 /* 0: no backward-data panels, no gradient buffers */
+  int side_stream;                   /* 1: each ResBlock's 1x1-skip backward runs on an internal high-priority stream
+                                        beside the conv2 -> GN2 -> conv1 chain (event fork / join: capturable) */
+} isb_unet_cfg;
+typedef struct isb_unet isb_unet;
+int isb_unet_create(const isb_unet_cfg* cfg, isb_unet** out);
+/* name: the reference's parameter name ("input_blocks.3.0.in_layers.2.weight", ...); the tensor is copied.  Optional
+ * extra entry "time_embed.freqs" [model_channels/2]: the host's own frequency table (nn.py:113-115). */
+int isb_unet_load_weight(isb_unet* h, const char* name, const void* dev_ptr, int dtype, const int64_t* shape, int ndim,
+                         isb_stream_t stream);
+/* Builds the plan and packs the weights; synchronises `stream`; names the first missing / mis-shaped parameter. */
+int isb_unet_finalize(isb_unet* h, isb_stream_t stream);
+size_t isb_unet_workspace_bytes(const isb_unet* h);
+/* Zero-fills the workspace (arrival counters, statistics partials) — once, before the first pass. */
+int isb_unet_workspace_init(isb_unet* h, void* workspace, size_t workspace_bytes, isb_stream_t stream);
+int isb_unet_num_blocks(const isb_unet* h);   /* len(output_blocks): valid feat_layer values are [0, n) */
+/* x_nchw [N,in_channels,H,W] fp32, t [N] fp32 timestep VALUES (after the respacing map).  out: [N,out_channels,H,W]
+ * (out_nhwc = 0) or [N,H,W,out_channels] (out_nhwc = 1), may be NULL.  stop_at_feat = 1 (needs feat_layer >= 0):
+ * return after output_blocks[feat_layer] — the guided step then runs isb_unet_forward_tail on a second stream beside
+ * the backward pass (separate scratch and split-K workspace slots are reserved for exactly that). */
+int isb_unet_forward(isb_unet* h, const float* x_nchw, const float* t, int feat_layer, int stop_at_feat, float* out,
+                     int out_nhwc, void* workspace, size_t workspace_bytes, isb_stream_t stream);
+int isb_unet_forward_tail(isb_unet* h, float* out, int out_nhwc, void* workspace, size_t workspace_bytes,
+                          isb_stream_t stream);
+/* The intermediate feature of unet.py:667-668 inside the workspace: val / grad are fp32 NHWC [dims] (grad NULL
+ * without want_backward).  isb_drag_loss_grad reads val and writes grad in place. */
+int isb_unet_feat(const isb_unet* h, void* workspace, int feat_layer, float** val, float** grad, int dims[4]);
+/* d(sum(d_feat o inter_feat) + sum(d_out o out)) / dx -> dx_nchw [N,in_channels,H,W] fp32.  d_feat_nhwc: gradient of
+ * the feature (copied in), or NULL with feat_grad_in_place = 1 when the caller already wrote it to isb_unet_feat's
+ * grad; d_out_nchw [N,out_channels,H,W] or NULL.  Must follow the forward it differentiates. */
+int isb_unet_backward_input(isb_unet* h, int feat_layer, const float* d_feat_nhwc, int feat_grad_in_place,
+                            const float* d_out_nchw, float* dx_nchw, void* workspace, size_t workspace_bytes,
+                            isb_stream_t stream);
+void isb_unet_destroy(isb_unet* h);
+
 /* ---- introspection ---------------------------------------------------- */
 /* Number of kernels this library has launched in this process (all threads). */
 uint64_t isb_launch_count(void);

@@ -111,6 +111,17 @@ class TrackDesc(C.Structure):
     ]
 
 
+class UnetCfg(C.Structure):
+    _fields_ = [
+        ("in_channels", c_int), ("model_channels", c_int), ("out_channels", c_int), ("num_res_blocks", c_int),
+        ("n_levels", c_int), ("channel_mult", c_int * 8),
+        ("n_attn", c_int), ("attention_ds", c_int * 8),
+        ("num_heads", c_int), ("num_head_channels", c_int), ("num_heads_upsample", c_int),
+        ("N", c_int), ("H", c_int), ("W", c_int),
+        ("mode", c_int), ("want_backward", c_int), ("side_stream", c_int),
+    ]
+
+
 # name -> (restype, argtypes); also the list the symbol-export test checks against the header
 PROTOTYPES = {
     "isb_abi_version": (c_int, []),
@@ -147,6 +158,19 @@ PROTOTYPES = {
     "isb_mc_emit": (c_int, [c_void_p, c_int, C.c_float, c_void_p, c_size_t, C.c_float, c_void_p, c_void_p, c_void_p]),
     "isb_mesh_smooth_workspace_bytes": (c_size_t, [C.c_int64, C.c_int64]),
     "isb_mesh_smooth_simple": (c_int, [c_void_p, C.c_int64, c_void_p, C.c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "isb_unet_create": (c_int, [C.POINTER(UnetCfg), C.POINTER(c_void_p)]),
+    "isb_unet_load_weight": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, C.POINTER(C.c_int64), c_int, c_void_p]),
+    "isb_unet_finalize": (c_int, [c_void_p, c_void_p]),
+    "isb_unet_workspace_bytes": (c_size_t, [c_void_p]),
+    "isb_unet_workspace_init": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "isb_unet_num_blocks": (c_int, [c_void_p]),
+    "isb_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t,
+                                 c_void_p]),
+    "isb_unet_forward_tail": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "isb_unet_feat": (c_int, [c_void_p, c_void_p, c_int, C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_int * 4)]),
+    "isb_unet_backward_input": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                        c_void_p]),
+    "isb_unet_destroy": (None, [c_void_p]),
     "isb_triplane_decode_grid": (c_int, [c_void_p, c_int, C.POINTER(TriplaneMlp), c_void_p, c_int, c_int, c_int,
                                          c_void_p, c_void_p]),
     "isb_triplane_decode_points": (c_int, [c_void_p, c_int, C.POINTER(TriplaneMlp), c_void_p, C.c_int64,

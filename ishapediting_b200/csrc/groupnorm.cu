@@ -12,6 +12,15 @@
 
 namespace isb {
 
+// The apply kernels are pure streaming passes: bytes in flight per SM = resident threads x bytes per thread.  With 76-80
+// registers only 3 CTAs of 256 threads fit (37.5 % occupancy: ncu --set full, profiles/r02_ncu_full_gn.md) and the
+// 512-CTA grid of a 128x128x256 layer ran as 1.15 waves; capping the registers at 64 (4 CTAs / SM) makes it one wave.
+// (Measured: the cap costs more in spills than the occupancy brings — 4.94 vs 4.88 ms per step — so the default stays 3.
+// Sizing gn_apply_part's pixel chunks so that its grid is ONE wave at 3 CTAs per SM (512 pixels per CTA at 128^2) was
+// measured too: 4.77 / 4.87 ms with and without alike, inside the box-to-box spread; not kept.)
+#ifndef GN_MIN_BLOCKS
+#define GN_MIN_BLOCKS 3
+#endif
 constexpr int GN_MAX_SPLITS = 64;
 constexpr int GN_MAX_NG = 4096;   // arrival counters at the head of the scratch buffer (N * groups <= 4096)
 
@@ -182,7 +191,7 @@ __device__ __forceinline__ void gn_apply_one(const GnArgs& a, const GnFwdOut& o,
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GN_MIN_BLOCKS)
 gn_apply_kernel(const GnArgs a, const GnFwdOut o) {
   pdl_wait();      // predecessor complete and flushed
   pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
@@ -207,7 +216,7 @@ gn_apply_kernel(const GnArgs a, const GnFwdOut o) {
 // group, then the 8 run sums in order), and goes on to apply.  No statistics pass, no finalize launch.
 // grid (pixel chunks, C/32, N), 256 threads: thread t owns channel vector t & 3 of pixels (t >> 2) + 64 j.
 constexpr int GN_PART_UNROLL = 4;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GN_MIN_BLOCKS)
 gn_apply_part_kernel(const GnArgs a, const GnFwdOut o, const float2* __restrict__ partials, int slots, int ppc) {
   pdl_wait();      // predecessor complete and flushed
   pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
@@ -489,7 +498,7 @@ __device__ __forceinline__ void gn_bwd_apply_one(const GnArgs& a, const GnBwdArg
   if (lo != nullptr) store8(lo, off, b.lo_dtype, dx);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GN_MIN_BLOCKS)
 gn_bwd_apply_kernel(const GnArgs a, const GnBwdArgs b) {
   pdl_wait();      // predecessor complete and flushed
   pdl_trigger();   // only now may the successor become resident (no cascade of waiting grids)
