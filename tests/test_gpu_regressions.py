@@ -170,3 +170,43 @@ def test_plans_of_different_batch_share_groupnorm_scratch(mode):
         assert rel_l2(f4b[k:k + 1], singles[k][1]) < tol, k
     for k in range(2):
         assert rel_l2(o2[k:k + 1], singles[k][0]) < tol, k
+
+
+def test_repeated_edits_are_deterministic_and_do_not_grow_memory():
+    """The editor runs many drags on one loaded shape (main.py:447-451 calls training() per drag).  The same drag
+    repeated must give the same bits (fixed-order reductions, no atomics on the step path), a different drag in
+    between must not disturb it (static buffers are re-targeted, the captured graph is reused), and device memory
+    must stay flat from the second edit on (no per-edit allocations that are never released)."""
+    from ishapediting_b200.drag_utils import DragStuff, get_args
+
+    cfg = O.mid_cfg()
+    cfg.update(in_out_channels=96, timestep_respacing="20")
+    sd = O.synth_state_dict(cfg)
+    a = get_args(["--num_steps", "20", "--w_time", "4", "--shape_resolution", "64", "--feat_layer", "5", "--resolution", "32"])
+    a.channel_mult, a.attention_resolutions, a.use_fp16 = "1,2,4", "16,8", True
+    ds = DragStuff(args=a, device=DEV, use_graph=True)
+    ds.model.load_state_dict(sd)
+    ds.model.to(DEV).eval()
+    ds.set_offset1(4)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 96, 32, 32, generator=g)
+    noise = torch.randn(1, 96, 32, 32, generator=g).to(DEV)
+    src = (torch.rand(3, 3, generator=g) - 0.5).numpy()
+    tgt = src + (torch.rand(3, 3, generator=g).numpy() - 0.5) * 0.4
+    ds.update_latent_params(x.to(DEV), noise=noise)
+
+    def edit(s, t, scale):
+        list(ds.training(s, t, scale=scale, cof=0.2, noises=[noise] * 4))
+        torch.cuda.synchronize()
+        return ds.stepper.img.clone(), ds.last_volume.clone()
+
+    img0, vol0 = edit(src, tgt, 600)
+    edit(src[::-1].copy(), tgt[::-1].copy(), 300)          # another drag in between
+    torch.cuda.synchronize()
+    mem = []
+    for k in range(6):
+        img, vol = edit(src, tgt, 600)
+        assert torch.equal(img, img0) and torch.equal(vol, vol0), k
+        del img, vol
+        mem.append(torch.cuda.memory_allocated())
+    assert max(mem[1:]) == min(mem[1:]), mem
