@@ -1,6 +1,8 @@
 """Which convolution classes sit on the critical path of the graph-replayed guided step?  Re-capture the step with the
 convs of ONE class (by spatial size / role) stubbed out and report the time they cost in-graph (not cold, not
-serialised like the ncu launch list).   python tools/ablate_conv_classes.py"""
+serialised like the ncu launch list).   python tools/ablate_conv_classes.py [--batch B]
+With --batch B the step advances B independent edits (the throughput mode); the GroupNorm and attention families are
+ablated the same way."""
 import os
 import sys
 
@@ -14,6 +16,7 @@ from ishapediting_b200.drag_utils import DragGeometry, GuidedStepper
 
 
 def main():
+    B = int(sys.argv[sys.argv.index("--batch") + 1]) if "--batch" in sys.argv else 1
     dev = "cuda:0"
     cfg = O.NFD_CFG
     model, diff = build_model(cfg, O.synth_state_dict(cfg), "bf16", dev)
@@ -21,9 +24,11 @@ def main():
     src = rng.uniform(-0.5, 0.5, size=(4, 3)).astype(np.float32)
     tgt = (src + rng.uniform(-0.2, 0.2, size=(4, 3))).astype(np.float32)
     geo = DragGeometry(src, tgt, 12, 2.0 / 256, 64, 170)
+    if B > 1:
+        geo = [geo] * B
     g = torch.Generator().manual_seed(1)
-    x = torch.randn(1, 96, 128, 128, generator=g).to(dev)
-    origin = torch.randn(3, 64, 64, 170, generator=g).to(dev)
+    x = torch.randn(B, 96, 128, 128, generator=g).to(dev)
+    origin = torch.randn(*((B,) if B > 1 else ()), 3, 64, 64, 170, generator=g).to(dev)
     ops = model._get_ops()
     orig = ops.conv
     stats = {}
@@ -76,6 +81,18 @@ def main():
                       f"{gf / max(d, 1e-6):7.1f} TF/s in-graph)")
     t, snap = run(lambda h, k: True)
     print(f"all convs: cost {full - t:.3f} ms")
+    noop = lambda *a, **kw: None     # noqa: E731
+    for fam, names in (("GroupNorm", ("gn_forward", "gn_backward")),
+                       ("attention", ("attention_flash_forward", "attention_flash_backward"))):
+        saved = {n: getattr(ops, n) for n in names}
+        for n in names:
+            setattr(ops, n, noop)
+        try:
+            t, _ = run(lambda H, k: False)
+        finally:
+            for n, f in saved.items():
+                setattr(ops, n, f)
+        print(f"{fam}: cost {full - t:.3f} ms")
     full2, _ = run(lambda H, k: False)
     print(f"full step again {full2:.3f} ms")
     os._exit(0)
