@@ -18,6 +18,11 @@ namespace isb {
 // (Measured: the cap costs more in spills than the occupancy brings — 4.94 vs 4.88 ms per step — so the default stays 3.
 // Sizing gn_apply_part's pixel chunks so that its grid is ONE wave at 3 CTAs per SM (512 pixels per CTA at 128^2) was
 // measured too: 4.77 / 4.87 ms with and without alike, inside the box-to-box spread; not kept.)
+// Also measured and dropped (round 2, A/B of two builds on one box, interleaved): folding the conv-epilogue partials with
+// one warp per group (one L2 round trip instead of four) + the wide-load part kernel for the two-source GroupNorms +
+// an unrolled backward reduce: batch-1 step 4.94 vs 4.88 ms (slower), batch-8 step 17.84 vs 17.85 ms (no change) —
+// although ncu shows these kernels at 2.5-2.8 TB/s with 33-37 % occupancy when run alone at batch 8
+// (gpurun_out -> profiles/r02_ncu_gn_batch8.md), inside the graph they are not what the step waits for.
 #ifndef GN_MIN_BLOCKS
 #define GN_MIN_BLOCKS 3
 #endif

@@ -70,7 +70,7 @@ def main():
     run(lambda H, k: True)
     full, _ = run(lambda H, k: False)
     print(f"full step {full:.3f} ms")
-    for H in (8, 16, 32, 64, 128):
+    for H in (() if "--only-full" in sys.argv else (8, 16, 32, 64, 128)):
         for ks in (3, 1):
             t, snap = run(lambda h, k, H=H, ks=ks: h == H and k == ks)
             n = sum(v[0] for v in snap.values())
@@ -79,8 +79,9 @@ def main():
                 d = full - t
                 print(f"H={H:3d} k{ks}: {n:3d} launches {gf:7.1f} GFLOP  cost {d:6.3f} ms  ({1e3 * d / n:5.1f} us/launch, "
                       f"{gf / max(d, 1e-6):7.1f} TF/s in-graph)")
-    t, snap = run(lambda h, k: True)
-    print(f"all convs: cost {full - t:.3f} ms")
+    if "--only-full" not in sys.argv:
+        t, snap = run(lambda h, k: True)
+        print(f"all convs: cost {full - t:.3f} ms")
     noop = lambda *a, **kw: None     # noqa: E731
     for fam, names in (("GroupNorm", ("gn_forward", "gn_backward")),
                        ("attention", ("attention_flash_forward", "attention_flash_backward"))):

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--time-ops", action="store_true", help="CUDA-event time per op family (eager)")
     ap.add_argument("--algbytes", default=None, help="write per-family algorithmic bytes of one step to this JSON")
+    ap.add_argument("--batch", type=int, default=1, help="advance this many independent edits as one batch")
     ap.add_argument("--decode", type=int, default=0, help="also profile one dense decode at this resolution")
     args = ap.parse_args()
     dev = "cuda:0"
@@ -30,10 +31,11 @@ def main():
     src = rng.uniform(-0.5, 0.5, size=(4, 3)).astype(np.float32)
     tgt = (src + rng.uniform(-0.2, 0.2, size=(4, 3))).astype(np.float32)
     geo = DragGeometry(src, tgt, 12, 2.0 / 256, 64, 170)
-    st = GuidedStepper(model, diff, geo, 8, 0.2, "l2", 600.0, use_graph=False)
+    B = args.batch
+    st = GuidedStepper(model, diff, [geo] * B if B > 1 else geo, 8, 0.2, "l2", 600.0, use_graph=False)
     g = torch.Generator().manual_seed(1)
-    st.img.copy_(torch.randn(1, 96, 128, 128, generator=g).to(dev))
-    origin = torch.randn(3, 64, 64, 170, generator=g).to(dev)
+    st.img.copy_(torch.randn(B, 96, 128, 128, generator=g).to(dev))
+    origin = torch.randn(*((B,) if B > 1 else ()), 3, 64, 64, 170, generator=g).to(dev)
     st.step(49, origin)          # warm-up (sizes workspaces)
     torch.cuda.synchronize()
     if args.time_ops:
