@@ -534,6 +534,8 @@ class _UNetFn(th.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, model, plan, t_orig, feat_layer):
+        if hasattr(ctx, "set_materialize_grads"):
+            ctx.set_materialize_grads(False)      # an unused output gets None, not a zero tensor that drives a backward branch
         inter = plan.forward(x.detach().to(th.float32).contiguous(), t_orig, feat_layer)
         ctx.plan, ctx.gen, ctx.inter, ctx.shape = plan, plan.generation, inter, x.shape
         N, C2, H, W = plan.N, plan.out_nhwc.shape[3], plan.H, plan.W
@@ -562,6 +564,43 @@ class _UNetFn(th.autograd.Function):
             plan.seed_grad(ctx.inter, g_nhwc)
         dx = plan.ops.empty(tuple(ctx.shape))
         plan.backward(dx)
+        return dx, None, None, None, None
+
+
+class _NativeUNetFn(th.autograd.Function):
+    """The same bridge over the handle-level C ABI (native_unet.NativeUNet / csrc/unet.cu): the whole pass is ONE
+    library call, so the eager public API is GPU-bound (5.4 ms per NFD forward + backward where the per-operator
+    Python plan needs 9 ms of host time).  Bit-identical to `_UNetFn` (tests/test_gpu_native_unet.py)."""
+
+    @staticmethod
+    def forward(ctx, x, model, nat, t_orig, feat_layer):
+        if hasattr(ctx, "set_materialize_grads"):
+            ctx.set_materialize_grads(False)
+        ops = model._get_ops()
+        nat.generation = getattr(nat, "generation", 0) + 1
+        out = nat.forward(x.detach().to(th.float32).contiguous(), t_orig, feat_layer=feat_layer)
+        ctx.nat, ctx.gen, ctx.feat_layer, ctx.shape, ctx.ops = nat, nat.generation, feat_layer, x.shape, ops
+        if feat_layer < 0:
+            return out
+        val, _ = nat.feat(feat_layer)
+        Ni, Hi, Wi, Ci = val.shape
+        feat = ops.to_nchw(val, ops.empty((Ni, Ci, Hi, Wi)))
+        return out, feat
+
+    @staticmethod
+    def backward(ctx, *grads):
+        nat, ops = ctx.nat, ctx.ops
+        if nat.generation != ctx.gen:
+            raise RuntimeError("UNetModel.backward: the plan's activations were overwritten by a later forward; "
+                               "call backward before the next forward (the reference loop does)")
+        g_out = grads[0]
+        g_feat = grads[1] if len(grads) > 1 else None
+        d_feat = None
+        if g_feat is not None and ctx.feat_layer >= 0:
+            Ni, Ci, Hi, Wi = g_feat.shape
+            d_feat = ops.to_nhwc(g_feat.to(th.float32).contiguous(), ops.empty((Ni, Hi, Wi, Ci)))
+        d_out = g_out.to(th.float32).contiguous() if g_out is not None else None
+        dx = nat.backward_input(ctx.feat_layer if d_feat is not None else -1, d_feat=d_feat, d_out=d_out)
         return dx, None, None, None, None
 
 
@@ -650,6 +689,7 @@ class UNetModel(nn.Module):
         self.out = nn.Sequential(normalization(ch), nn.SiLU(),
                                  zero_module(conv_nd(dims, input_ch, out_channels, 3, padding=1)))
         self._plans = {}
+        self._native = {}
         self._ops = None
         self._mode = "bf16" if use_fp16 else "fp32"
         self.weights_generation = 0      # bumped whenever packed weight panels (plans) become stale
@@ -677,6 +717,7 @@ class UNetModel(nn.Module):
         """Parameters, precision mode or backend changed: drop every plan (their weight panels are packed COPIES) and
         tell whoever cached one (GuidedStepper and its captured graph, FiLM rows) through `weights_generation`."""
         self._plans = {}
+        self._native = {}
         self.weights_generation = getattr(self, "weights_generation", 0) + 1
 
     def load_state_dict(self, *a, **kw):
@@ -711,13 +752,36 @@ class UNetModel(nn.Module):
             self._plans[key] = p
         return p
 
+    def _native_plan(self, N, H, W):
+        """The handle-level plan for the eager API (None when switched off with ISB_NATIVE_EAGER=0 or when a non-CUDA
+        operator backend was injected by a test).  The steppers (GuidedStepper, ReconStepper, the no-grad step graph)
+        keep the per-operator plan, which they capture into CUDA graphs."""
+        if os.environ.get("ISB_NATIVE_EAGER", "1") == "0" or getattr(self._get_ops(), "name", "") != "cuda":
+            return None
+        if self.training and self.dropout > 0:
+            raise NotImplementedError("dropout>0 in training mode is not implemented: call model.eval() "
+                                      "(the editor always does, drag_utils.py:187)")
+        key = (N, H, W, self._mode)
+        nat = self._native.get(key)
+        if nat is None:
+            from ..native_unet import NativeUNet
+            nat = NativeUNet(self, N, H, W, mode=self._mode, want_backward=True)
+            self._native[key] = nat
+        return nat
+
     def forward(self, x, timesteps, y=None, feat_layer=-1):
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
         N, _, H, W = x.shape
         need_grad = th.is_grad_enabled() and x.requires_grad
-        plan = self.plan(N, H, W, want_backward=True)
         t_orig = timesteps.to(device=x.device, dtype=th.float32).contiguous()   # may be fractional (rescale_timesteps)
+        nat = self._native_plan(N, H, W)
+        if nat is not None:          # eager public API: the whole pass is one call into the library (csrc/unet.cu)
+            if need_grad:
+                return _NativeUNetFn.apply(x, self, nat, t_orig, feat_layer)
+            with th.no_grad():
+                return _NativeUNetFn.forward(_NoCtx(), x, self, nat, t_orig, feat_layer)
+        plan = self.plan(N, H, W, want_backward=True)
         if need_grad:
             return _UNetFn.apply(x, self, plan, t_orig, feat_layer)
         with th.no_grad():

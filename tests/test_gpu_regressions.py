@@ -25,10 +25,11 @@ def _stepper_case(mode="bf16"):
     return cfg, sd, model, diff, st, x.to(DEV), origin_d, noise.to(DEV), (src, tgt, r1, voxel)
 
 
-def test_captured_graph_survives_a_larger_batch_plan():
+def test_captured_graph_survives_a_larger_batch_plan(monkeypatch):
     """A graph captured at batch 1 keeps raw pointers to the shared GroupNorm scratch / split-K workspace.  A later
     batch-8 pass (ddpm_inversion(batch=8), a batch-8 stepper) outgrows those buffers; the batch-1 graph must still
     replay correctly afterwards (the outgrown buffers are retired, never freed)."""
+    monkeypatch.setenv("ISB_NATIVE_EAGER", "0")     # the eager passes below must go through the SHARED per-operator buffers
     cfg, sd, model, diff, st, x, origin, noise, _ = _stepper_case()
     for _ in range(3):                      # warm-up, capture, replay
         st.img.copy_(x)
@@ -146,10 +147,11 @@ def test_fractional_timesteps_are_embedded_as_floats():
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-def test_plans_of_different_batch_share_groupnorm_scratch(mode):
+def test_plans_of_different_batch_share_groupnorm_scratch(mode, monkeypatch):
     """The GroupNorm scratch buffer is shared by every plan of a model.  Its arrival counters must not move with
     the batch size: with an N-dependent layout a batch-1 pass left partial sums where a batch-4 pass keeps the
     counters of images 1..3, and those images then got wrong statistics (found by test_latent_inversion_nfd)."""
+    monkeypatch.setenv("ISB_NATIVE_EAGER", "0")     # per-operator plans (the handle-level plan owns its scratch)
     cfg = O.mid_cfg()
     sd = O.synth_state_dict(cfg)
     model, _ = build_model(cfg, sd, mode, DEV)

@@ -30,10 +30,14 @@ def _unet_case(cfg, mode, t_val=246):
                 grad=rel_l2(xd.grad, xr.grad))
 
 
+@pytest.mark.parametrize("native", ["1", "0"])
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-def test_unet_mid_forward_backward(mode):
+def test_unet_mid_forward_backward(mode, native, monkeypatch):
+    """The public `UNetModel.forward` + autograd: through the handle-level plan (default) and through the per-operator
+    Python plan (ISB_NATIVE_EAGER=0, what the steppers capture)."""
+    monkeypatch.setenv("ISB_NATIVE_EAGER", native)
     errs = _unet_case(O.mid_cfg(), mode)
-    print("mid", mode, errs)
+    print("mid", mode, "native" if native == "1" else "python plan", errs)
     assert max(errs.values()) < TOL[mode], errs
 
 
