@@ -84,7 +84,10 @@ def test_slab_sharded_decode_and_edit_gather_world2(res, n_edits):
     w, planes = O.synth_decoder(R=32)
     ref = O.decode_grid(w, planes, res).view(res, res, res)
     assert vol.shape == ref.shape
-    assert float((vol - ref).abs().max()) < 1e-5          # disjoint slabs: no reduction-order issue
+    # The gather itself is exact (vol == vol2 below, and each rank only contributes its own disjoint slab); the slabs
+    # are computed by the torch mirror in a 2-thread worker and the reference here with the main process's thread
+    # count, and BLAS reduction order moves these fp32 logits by up to ~2e-5 (the Fourier features amplify rounding).
+    assert float((vol - ref).abs().max()) < 1e-4
     assert torch.equal(vol, vol2)
     assert torch.equal(allr, torch.tensor([[float(k), float(k * k)] for k in range(n_edits)]))
 
