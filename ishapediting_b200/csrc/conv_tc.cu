@@ -1150,12 +1150,20 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   //    launch drains (programmatic dependent launch): their prologue and weight prefetch overlap our epilogue.
   //    Deeper pipelines (6 stages, 144-192 KB) measured up to 2x slower in a chain of launches for that reason.
   const int sms = num_sms();
+  // policy knobs (experiments only; the defaults are the tuned values)
+  auto knob = [](const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+  };
+  const int cta_factor = knob("ISB_TC_CTA_FACTOR", 2), need_few = knob("ISB_TC_NEED_FEW", 2),
+            need_many = knob("ISB_TC_NEED_MANY", 8), small_bn = knob("ISB_TC_SMALL_BN", 64),
+            max_split = knob("ISB_TC_MAX_SPLIT", 8);
   auto splits_for = [&](int tiles) {
     int sp = 1;
-    const int need = tiles >= 48 ? 8 : 2;
-    while (sp < 8) {
+    const int need = tiles >= 48 ? need_many : need_few;
+    while (sp < max_split) {
       const int next = sp * 2;
-      if (static_cast<long long>(tiles) * next > 2LL * sms || p.k_iters / next < need) break;
+      if (static_cast<long long>(tiles) * next > static_cast<long long>(cta_factor) * sms || p.k_iters / next < need) break;
       sp = next;
     }
     return sp;
@@ -1164,7 +1172,7 @@ static int plan_tc(const isb_conv_desc* d, TcPlan* plan) {
   if (bn == 0) {
     if (d->Cout < 128) bn = d->Cout;                                  // 32,64,96
     else if (d->Cout % 128 != 0 && d->Cout <= 256) bn = d->Cout;      // e.g. 192: one exact tile
-    else bn = ((d->ksize == 1 || mtiles <= 2) && d->Cout % 64 == 0) ? 64 : 128;   // 1x1 / tiny images: 64-wide
+    else bn = ((d->ksize == 1 || mtiles <= 2) && d->Cout % 64 == 0) ? small_bn : 128;   // 1x1 / tiny images: 64-wide
     if (bn == 64 && d->Cout % 128 == 0 && static_cast<long long>(mtiles) * (d->Cout / 64) > 2LL * sms)
       bn = 128;       // already more 64-wide tiles than two waves (batched launches): wider tiles re-read A less
   }

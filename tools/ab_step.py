@@ -30,6 +30,8 @@ def main():
         for kv in v.split():
             k, val = kv.split("=")
             os.environ[k] = val
+        if "ISB_TC_" in v:
+            model.invalidate()      # conv tiling policy changed: the plan's statistics slots depend on it
         st = GuidedStepper(model, diff, geo, 8, 0.2, "l2", 600.0, use_graph=True)
         st.img.copy_(x)
         for k in range(50):
