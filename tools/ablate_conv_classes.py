@@ -84,7 +84,8 @@ def main():
         print(f"all convs: cost {full - t:.3f} ms")
     noop = lambda *a, **kw: None     # noqa: E731
     for fam, names in (("GroupNorm", ("gn_forward", "gn_backward")),
-                       ("attention", ("attention_flash_forward", "attention_flash_backward"))):
+                       ("attention", ("attention_flash_forward", "attention_flash_backward")),
+                       ("drag loss + gradient", ("drag_loss_grad",))):
         saved = {n: getattr(ops, n) for n in names}
         for n in names:
             setattr(ops, n, noop)
