@@ -63,3 +63,30 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in re.sub(r'""".*?"""', "", text, flags=re.S).replace("# oracle", ""), \
                     f"{f} references the oracle"
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="library not built")
+def test_handle_level_abi_refuses_to_run_without_a_device():
+    """The handle-level entry points fail loudly, with a message, before isb_init() has bound a B200 — no silent
+    host fallback (this box has no GPU; on a GPU box the same calls are exercised by tests/test_gpu_native_unet.py)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ishapediting_b200 import _lib
+
+    lib = _lib.load()
+    cfg = _lib.UnetCfg()
+    cfg.in_channels, cfg.model_channels, cfg.out_channels, cfg.num_res_blocks = 96, 256, 192, 2
+    cfg.n_levels = 1
+    cfg.channel_mult[0] = 1
+    cfg.num_heads, cfg.num_head_channels, cfg.num_heads_upsample = 1, 64, -1
+    cfg.N, cfg.H, cfg.W, cfg.mode, cfg.want_backward = 1, 32, 32, _lib.BF16, 1
+    h = ctypes.c_void_p()
+    rc = lib.isb_unet_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc != 0 and not h.value
+    assert b"isb_init" in lib.isb_last_error()
+    assert lib.isb_unet_workspace_bytes(None) == 0 and lib.isb_unet_num_blocks(None) == 0
+    lib.isb_unet_destroy(None)          # a null handle is accepted
+    with pytest.raises(_lib.IsbError):
+        _lib.init(0)                    # no sm_100 device here
