@@ -159,6 +159,41 @@ def test_latent_inversion_nfd(mode):
     assert e0 < tol
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_latent_inversion_nfd_full_length(mode):
+    """BASELINE configs[2] with the reference's default w_time = 170 (drag_utils.py:56), where the stepwise CPU oracle
+    (170 NFD forwards) is out of reach for a test: size-independent properties instead.  (i) `sample` is x_0 up to
+    one rounding; (ii) inversion followed by re-sampling is the identity: 170 batch-1 `p_sample_guidance` steps on
+    the device from `latent`, fed the stored variance_noise (the editor's loop with zero guidance,
+    drag_utils.py:341-350), land on x_0 although the inversion evaluated the UNet in batches of 8."""
+    from ishapediting_b200.drag_utils import DragStuff, get_args
+
+    cfg = O.NFD_CFG
+    sd = O.synth_state_dict(cfg)
+    a = get_args(["--num_steps", "200", "--w_time", "170", "--shape_resolution", "32"])
+    a.use_fp16 = (mode == "bf16")
+    ds = DragStuff(args=a, device=DEV, use_graph=True)
+    ds.model.load_state_dict(sd)
+    ds.model.to(DEV).eval()
+    g = torch.Generator().manual_seed(6)
+    x0 = (torch.randn(1, 96, 128, 128, generator=g) * 0.5).clamp(-1, 1).to(DEV)
+    torch.manual_seed(12)
+    with torch.no_grad():
+        outs = ds.diffusion.ddpm_inversion(ds.model, x0, 170, clip_denoised=True, feat_layer=cfg["feat_layer"])
+        assert len(outs["inter_feat"]) == len(outs["variance_noise"]) == len(outs["variance"]) == 170
+        ulp = float(np.finfo(np.float32).eps)
+        scale = float(torch.maximum(outs["variance_noise"][-1].abs(), x0.abs()).max())
+        assert float((outs["sample"] - x0).abs().max()) <= 2 * ulp * max(scale, 1.0)
+        img = outs["latent"]
+        for k, i in enumerate(range(169, -1, -1)):
+            t = torch.tensor([i], device=DEV)
+            img = ds.diffusion.p_sample_guidance(ds.model, img, t, variance_noise=outs["variance_noise"][k],
+                                                 clip_denoised=True)["sample"]
+    e0 = rel_l2(img, x0)
+    print("nfd inversion w_time=170", mode, "inversion -> re-sampling recovers x0 to", e0)
+    assert e0 < TOL[mode]
+
+
 def test_decoder_matches_reference_golden():
     """The CUDA decoder against the reference's own MultiTriplane.forward outputs (tests/golden/decoder.npz)."""
     from ishapediting_b200.triplane_decoder.visualize import query_volume
