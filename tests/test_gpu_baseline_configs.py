@@ -326,10 +326,11 @@ def test_decoder_ragged_point_counts(npts):
         assert float((out - ref).abs().max()) < 1e-4
 
 
-@pytest.mark.parametrize("res", [48, 130, 384])
+@pytest.mark.parametrize("res", [48, 130, 256, 384, 512])
 def test_decoder_grid_paths_agree_with_point_queries(res):
     """Dense-grid decode at resolutions that take the per-point sampling path (res % 128 != 0) and the cooperative row
-    path (res % 128 == 0): both must equal the arbitrary-points kernel on the same coordinates, slab by slab."""
+    path (res % 128 == 0, incl. BASELINE configs[3]'s 256 and 512): both must equal the arbitrary-points kernel on the same
+    coordinates, slab by slab."""
     from ishapediting_b200.triplane_decoder.visualize import query_volume
 
     dec, w, planes = build_decoder(128, DEV)
