@@ -23,6 +23,8 @@ namespace isb {
 // an unrolled backward reduce: batch-1 step 4.94 vs 4.88 ms (slower), batch-8 step 17.84 vs 17.85 ms (no change) —
 // although ncu shows these kernels at 2.5-2.8 TB/s with 33-37 % occupancy when run alone at batch 8
 // (gpurun_out -> profiles/r02_ncu_gn_batch8.md), inside the graph they are not what the step waits for.
+// What DID pay at batch 8 is the whole-row geometry further down (gn_apply_rows_kernel and its backward siblings, used
+// for tensors >= 64 MB only): 4.1 / 5.5 / 3.4 TB/s instead of 2.5-2.75 / 4.2 / 2.5, batch-8 step 17.31 vs 17.90 ms.
 #ifndef GN_MIN_BLOCKS
 #define GN_MIN_BLOCKS 3
 #endif
@@ -302,6 +304,84 @@ gn_apply_part_kernel(const GnArgs a, const GnFwdOut o, const float2* __restrict_
           y[j] = a.silu ? silu_f(z) : z;
         }
         const size_t off = (static_cast<size_t>(n) * a.HW + (p + u * 64)) * a.C + c0;
+        store8(o.y, off, o.y_dtype, y);
+        if (o.raw) store8(o.raw, off, o.raw_dtype, x[u]);
+      }
+  }
+}
+
+// ---- large tensors (beyond L2: the throughput mode, batch >= 4 at 64^2 / 128^2) ---------------------------------
+// There the apply pass is an HBM stream and what counts is bytes in flight and DRAM locality.  ncu at batch 8
+// (profiles/r02_ncu_gn_batch8.md): the 32-channel-column geometry above reaches 2.5 TB/s (a warp touches eight 128 B
+// pieces 1 KB apart, and every CTA first waits for its partial fold), the one-vector-per-thread kernel 2.75 TB/s (32 B
+// in flight per thread), while the kernels that read whole rows with several loads in flight reach 4.2 TB/s.  So:
+// statistics first (one warp per (image, group) folds the conv-epilogue partials), then whole pixel rows — thread =
+// (channel vector, pixel row), consecutive threads = consecutive 32 B of one pixel — with GN_ROWS_UNROLL pixels in flight.
+__global__ void __launch_bounds__(256)
+gn_fold_stats_kernel(const GnArgs a, const float2* __restrict__ partials, int slots) {
+  pdl_wait();
+  pdl_trigger();
+  const int ng = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (ng >= a.N * a.groups) return;
+  double s0 = 0, s1 = 0;
+  for (int i = threadIdx.x & 31; i < slots; i += 32) {
+    const float2 w = __ldcg(partials + static_cast<size_t>(ng) * slots + i);
+    s0 += w.x;
+    s1 += w.y;
+  }
+  s0 = warp_sum_d(s0);
+  s1 = warp_sum_d(s1);
+  if ((threadIdx.x & 31) == 0) {
+    const double m = static_cast<double>(a.HW) * a.Cg;
+    const double mean = s0 / m;
+    double var = s1 / m - mean * mean;
+    if (var < 0) var = 0;
+    a.stats[ng * 2 + 0] = static_cast<float>(mean);
+    a.stats[ng * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  }
+}
+
+constexpr int GN_ROWS_UNROLL = 4;
+// grid (pixel chunks, N), block = (C/8) * rows threads
+__global__ void __launch_bounds__(512)
+gn_apply_rows_kernel(const GnArgs a, const GnFwdOut o, int rows, int ppc) {
+  pdl_wait();
+  pdl_trigger();
+  const int CV = a.C / 8;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
+  const int n = blockIdx.y;
+  const int c0 = cv * 8;
+  const int p0 = blockIdx.x * ppc;
+  const int p1 = min(a.HW, p0 + ppc);
+  float x[GN_ROWS_UNROLL][8];
+#pragma unroll
+  for (int u = 0; u < GN_ROWS_UNROLL; ++u)
+    if (p0 + r + u * rows < p1) gn_load_x8(a, n, p0 + r + u * rows, c0, x[u]);
+  float ga[8], be[8];
+  gn_affine8(a, n, c0, ga, be);
+  const int sg = n * a.groups + c0 / a.Cg;
+  const float mean = a.stats[sg * 2], rstd = a.stats[sg * 2 + 1];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {   // z = x * ga' + be'
+    ga[j] *= rstd;
+    be[j] -= mean * ga[j];
+  }
+  for (int p = p0 + r; p < p1; p += GN_ROWS_UNROLL * rows) {
+    if (p != p0 + r) {
+#pragma unroll
+      for (int u = 0; u < GN_ROWS_UNROLL; ++u)
+        if (p + u * rows < p1) gn_load_x8(a, n, p + u * rows, c0, x[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < GN_ROWS_UNROLL; ++u)
+      if (p + u * rows < p1) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(x[u][j], ga[j], be[j]);
+          y[j] = a.silu ? silu_f(z) : z;
+        }
+        const size_t off = (static_cast<size_t>(n) * a.HW + (p + u * rows)) * a.C + c0;
         store8(o.y, off, o.y_dtype, y);
         if (o.raw) store8(o.raw, off, o.raw_dtype, x[u]);
       }
@@ -629,6 +709,140 @@ gn_bwd_apply_part_kernel(const GnArgs a, const GnBwdArgs b, const float2* __rest
   }
 }
 
+// Backward reduction for large tensors (see gn_apply_rows_kernel): whole pixel rows with GN_ROWS_UNROLL pixels in
+// flight; a CTA covers ALL groups of a pixel chunk and writes one partial per group, the last CTA to arrive for a
+// group folds that group's partials in chunk order (deterministic).  grid (chunks <= GN_MAX_SPLITS, N).
+__global__ void __launch_bounds__(512)
+gn_bwd_reduce_rows_kernel(const GnArgs a, const GnBwdArgs b, int rows, int ppc, int chunks) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float2 vals[512];
+  __shared__ int s_last[64];
+  const int CV = a.C / 8;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int c0 = cv * 8;
+  const int p0 = chunk * ppc;
+  const int p1 = min(a.HW, p0 + ppc);
+  GnRowBwdConst k;
+  gn_affine8(a, n, c0, k.ga, k.be);
+  {
+    const int sg = n * a.groups + c0 / a.Cg;
+    k.mean = a.stats[sg * 2];
+    k.rstd = a.stats[sg * 2 + 1];
+  }
+  float s1 = 0.f, s2 = 0.f;
+  for (int p = p0 + r; p < p1; p += GN_ROWS_UNROLL * rows) {
+    float x[GN_ROWS_UNROLL][8], dy[GN_ROWS_UNROLL][8];
+#pragma unroll
+    for (int u = 0; u < GN_ROWS_UNROLL; ++u)
+      if (p + u * rows < p1) {
+        gn_load_x8(a, n, p + u * rows, c0, x[u]);
+        load8(b.dy + (static_cast<size_t>(n) * a.HW + (p + u * rows)) * a.C + c0, dy[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < GN_ROWS_UNROLL; ++u)
+      if (p + u * rows < p1) {
+        float dzg[8], xhat[8];
+        gn_row_bwd_terms(a, k, x[u], dy[u], dzg, xhat);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1 += dzg[j]; s2 = fmaf(dzg[j], xhat[j], s2); }
+      }
+  }
+  vals[threadIdx.x] = make_float2(s1, s2);
+  __syncthreads();
+  const int V = a.Cg / 8;
+  if (static_cast<int>(threadIdx.x) < a.groups) {
+    const int g = threadIdx.x, ng = n * a.groups + g;
+    double d0 = 0, d1 = 0;
+    for (int rr = 0; rr < rows; ++rr)
+      for (int v = 0; v < V; ++v) {
+        const float2 t = vals[rr * CV + g * V + v];
+        d0 += t.x;
+        d1 += t.y;
+      }
+    a.partials[static_cast<size_t>(ng) * GN_MAX_SPLITS + chunk] = make_double2(d0, d1);
+    __threadfence();
+    const int prev = atomicAdd(a.counters + ng, 1);
+    s_last[g] = (prev == chunks - 1);
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < a.groups && s_last[threadIdx.x]) {
+    __threadfence();
+    const int ng = n * a.groups + threadIdx.x;
+    const double2* pp = a.partials + static_cast<size_t>(ng) * GN_MAX_SPLITS;
+    double t0 = 0, t1 = 0;
+    for (int c = 0; c < chunks; ++c) {
+      const double2 w = __ldcg(pp + c);
+      t0 += w.x;
+      t1 += w.y;
+    }
+    a.counters[ng] = 0;  // leave the scratch zeroed for the next call
+    const double m = static_cast<double>(a.HW) * a.Cg;
+    a.bstats[ng * 2 + 0] = static_cast<float>(t0 / m);
+    a.bstats[ng * 2 + 1] = static_cast<float>(t1 / m);
+  }
+}
+
+// Backward apply for large tensors, same row geometry; two pixels (4-8 independent 32 B loads) in flight per thread.
+constexpr int GN_ROWS_UNROLL_BWD = 2;
+__global__ void __launch_bounds__(512)
+gn_bwd_apply_rows_kernel(const GnArgs a, const GnBwdArgs b, int rows, int ppc) {
+  pdl_wait();
+  pdl_trigger();
+  const int CV = a.C / 8;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
+  const int n = blockIdx.y;
+  const int c0 = cv * 8;
+  const int p0 = blockIdx.x * ppc;
+  const int p1 = min(a.HW, p0 + ppc);
+  GnRowBwdConst k;
+  gn_affine8(a, n, c0, k.ga, k.be);
+  const int sg = n * a.groups + c0 / a.Cg;
+  k.mean = a.stats[sg * 2];
+  k.rstd = a.stats[sg * 2 + 1];
+  const float m1 = a.bstats[sg * 2], m2 = a.bstats[sg * 2 + 1];
+  // destination of this thread's channels: first or second source of the concatenation
+  const bool first = c0 < a.C1;
+  float* gx = first ? b.gx1 : b.gx2;
+  void* lo = first ? b.gx1_lo : b.gx2_lo;
+  const bool acc = (first ? b.acc1 : b.acc2) && gx != nullptr;
+  const int Cd = first ? a.C1 : a.C2, cd = first ? c0 : c0 - a.C1;
+  if (gx == nullptr && lo == nullptr) return;
+  for (int p = p0 + r; p < p1; p += GN_ROWS_UNROLL_BWD * rows) {
+    float x[GN_ROWS_UNROLL_BWD][8], dy[GN_ROWS_UNROLL_BWD][8], rs[GN_ROWS_UNROLL_BWD][8], old[GN_ROWS_UNROLL_BWD][8];
+#pragma unroll
+    for (int u = 0; u < GN_ROWS_UNROLL_BWD; ++u)
+      if (p + u * rows < p1) {
+        const size_t pix = static_cast<size_t>(n) * a.HW + (p + u * rows);
+        gn_load_x8(a, n, p + u * rows, c0, x[u]);
+        load8(b.dy + pix * a.C + c0, dy[u]);
+        if (b.gres != nullptr) load8(b.gres + pix * a.C + c0, rs[u]);
+        if (acc) {
+          const float4* q = reinterpret_cast<const float4*>(gx + pix * Cd + cd);
+          const float4 u0 = q[0], u1 = q[1];
+          old[u][0] = u0.x; old[u][1] = u0.y; old[u][2] = u0.z; old[u][3] = u0.w;
+          old[u][4] = u1.x; old[u][5] = u1.y; old[u][6] = u1.z; old[u][7] = u1.w;
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < GN_ROWS_UNROLL_BWD; ++u)
+      if (p + u * rows < p1) {
+        float dzg[8], xhat[8], dx[8];
+        gn_row_bwd_terms(a, k, x[u], dy[u], dzg, xhat);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dx[j] = k.rstd * (dzg[j] - (m1 + xhat[j] * m2));
+          if (b.gres != nullptr) dx[j] += rs[u][j];
+          if (acc) dx[j] += old[u][j];
+        }
+        const size_t off = (static_cast<size_t>(n) * a.HW + (p + u * rows)) * Cd + cd;
+        if (gx != nullptr) store8(gx, off, ISB_F32, dx);
+        if (lo != nullptr) store8(lo, off, b.lo_dtype, dx);
+      }
+  }
+}
+
 // single-launch backward for small tensors (see gn_fused_fwd_kernel)
 __global__ void __launch_bounds__(512)
 gn_fused_bwd_kernel(const GnArgs a, const GnBwdArgs b) {
@@ -681,6 +895,22 @@ static long long gn_fused_max() {
     return e ? atoll(e) : 8192LL;
   }();
   return v;
+}
+// tensors at least this large (fp32 bytes) take the whole-row apply kernel (ISB_GN_ROWS_MIN_MB, default 64 MB: beyond
+// what stays in the 126 MB L2 together with the conv's operands; batch 1 never gets there)
+static bool gn_use_rows(const GnArgs& a) {
+  const char* e = getenv("ISB_GN_ROWS_MIN_MB");
+  const double min_mb = e ? atof(e) : 64.0;
+  if (min_mb < 0 || a.resample != 0) return false;
+  const int CV = a.C / 8;
+  if (CV % 32 != 0 || CV > 512) return false;
+  return static_cast<double>(a.N) * a.HW * a.C * 4.0 >= min_mb * 1048576.0;
+}
+static cudaError_t gn_launch_rows(const GnArgs& a, const GnFwdOut& o, cudaStream_t st) {
+  const int CV = a.C / 8;
+  const int rows = CV >= 256 ? 1 : 256 / CV;
+  const int ppc = rows * GN_ROWS_UNROLL * 4;          // four iterations per CTA
+  return launch(gn_apply_rows_kernel, dim3(cdiv(a.HW, ppc), a.N), dim3(CV * rows), 0, st, a, o, rows, ppc);
 }
 static bool gn_use_fused(const GnArgs& a) { return static_cast<long long>(a.HW) * a.Cg <= gn_fused_max(); }
 // CTAs per (image, group) for the fused kernels: enough CTAs to pull bandwidth, DSMEM fold of the partial sums
@@ -781,6 +1011,15 @@ int isb_gn_forward(const isb_gn_desc* d, void* scratch, isb_stream_t stream) {
     ISB_CHECK_ARG(d->x2 == nullptr && d->resample == 0 && d->partial_slots > 0 && d->groups == 32 &&
                       (a.Cg == 8 || a.Cg == 16 || a.Cg == 32),
                   "isb_gn_forward: fused statistics need a single source, no resample, 32 groups of 8/16/32 channels");
+    if (isb::gn_use_rows(a)) {
+      { isb::PdlFamily fam(0);
+        ISB_CUDA(isb::launch(isb::gn_fold_stats_kernel, dim3(isb::cdiv(a.N * a.groups, 8)), dim3(256), 0, st, a,
+                             reinterpret_cast<const float2*>(d->partials), d->partial_slots)); }
+      ISB_LAUNCH_CHECK();
+      { isb::PdlFamily fam(1); ISB_CUDA(isb::gn_launch_rows(a, o, st)); }
+      ISB_LAUNCH_CHECK();
+      return ISB_OK;
+    }
     const int ppc = 64 * isb::GN_PART_UNROLL;
     isb::PdlFamily fam(1);
     ISB_CUDA(isb::launch(isb::gn_apply_part_kernel, dim3(isb::cdiv(a.HW, ppc), a.C / 32, a.N), dim3(256), 0, st, a, o,
@@ -797,6 +1036,11 @@ int isb_gn_forward(const isb_gn_desc* d, void* scratch, isb_stream_t stream) {
   }
   { isb::PdlFamily fam(0); ISB_CUDA(isb::launch(isb::gn_stats_kernel, dim3(a.splits, a.groups, a.N), 256, 0, st, a)); }
   ISB_LAUNCH_CHECK();
+  if (isb::gn_use_rows(a)) {
+    { isb::PdlFamily fam(1); ISB_CUDA(isb::gn_launch_rows(a, o, st)); }
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+  }
   const int Ho = a.resample == 1 ? a.H / 2 : a.H, Wo = a.resample == 1 ? a.W / 2 : a.W;
   const long long total = static_cast<long long>(a.N) * Ho * Wo * (a.C / 8);
   { isb::PdlFamily fam(1); ISB_CUDA(isb::launch(isb::gn_apply_kernel, isb::cdiv(total, 256), 256, 0, st, a, o)); }
@@ -832,8 +1076,29 @@ int isb_gn_backward(const isb_gn_bwd_desc* d, void* scratch, isb_stream_t stream
     ISB_LAUNCH_CHECK();
     return ISB_OK;
   }
-  { isb::PdlFamily fam(0); ISB_CUDA(isb::launch(isb::gn_bwd_reduce_kernel, dim3(a.splits, a.groups, a.N), 256, 0, st, a, b)); }
+  if (isb::gn_use_rows(a) && a.groups <= 64) {
+    const int CV = a.C / 8;
+    const int rows = CV >= 256 ? 1 : 256 / CV;
+    const int step = rows * isb::GN_ROWS_UNROLL;
+    int ppc = isb::cdiv(a.HW, isb::GN_MAX_SPLITS);
+    ppc = isb::cdiv(ppc, step) * step;
+    const int chunks = isb::cdiv(a.HW, ppc);
+    isb::PdlFamily fam(0);
+    ISB_CUDA(isb::launch(isb::gn_bwd_reduce_rows_kernel, dim3(chunks, a.N), dim3(CV * rows), 0, st, a, b, rows, ppc, chunks));
+  } else {
+    isb::PdlFamily fam(0);
+    ISB_CUDA(isb::launch(isb::gn_bwd_reduce_kernel, dim3(a.splits, a.groups, a.N), 256, 0, st, a, b));
+  }
   ISB_LAUNCH_CHECK();
+  if (isb::gn_use_rows(a)) {
+    const int CV = a.C / 8;
+    const int rows = CV >= 256 ? 1 : 256 / CV;
+    const int ppc = rows * isb::GN_ROWS_UNROLL_BWD * 4;
+    isb::PdlFamily fam(1);
+    ISB_CUDA(isb::launch(isb::gn_bwd_apply_rows_kernel, dim3(isb::cdiv(a.HW, ppc), a.N), dim3(CV * rows), 0, st, a, b, rows, ppc));
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+  }
   const long long total = static_cast<long long>(a.N) * a.HW * (a.C / 8);
   { isb::PdlFamily fam(1); ISB_CUDA(isb::launch(isb::gn_bwd_apply_kernel, isb::cdiv(total, 256), 256, 0, st, a, b)); }
   ISB_LAUNCH_CHECK();

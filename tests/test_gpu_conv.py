@@ -47,9 +47,13 @@ GN_STAT_CASES = [
 
 
 @pytest.mark.parametrize("case", GN_STAT_CASES, ids=[f"n{c[0]}_h{c[1]}_{c[2]}to{c[3]}_k{c[4]}_{i}" for i, c in enumerate(GN_STAT_CASES)])
-def test_conv_fused_groupnorm_statistics(ops_by_mode, case):
+@pytest.mark.parametrize("rows_mb", [None, "0"], ids=["default", "row-kernel"])
+def test_conv_fused_groupnorm_statistics(ops_by_mode, case, rows_mb, monkeypatch):
     """The conv epilogue's (sum, sum of squares) partials per (image, 32 groups) against the tensor it wrote, and
-    through gn_forward(partials=...) against the ordinary statistics pass."""
+    through gn_forward(partials=...) against the ordinary statistics pass.  rows_mb = "0" forces the large-tensor
+    route (statistics fold kernel + whole-row apply kernel) at these sizes."""
+    if rows_mb is not None:
+        monkeypatch.setenv("ISB_GN_ROWS_MIN_MB", rows_mb)
     ops = ops_by_mode["bf16"]
     N, H, Cin, Cout, k, Cin2, res, tune = case
     dev = ops.device

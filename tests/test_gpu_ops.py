@@ -53,8 +53,14 @@ GN_CASES = [
 ]
 
 
+@pytest.mark.parametrize("rows_mb", [None, "0"], ids=["default", "row-kernel"])
 @pytest.mark.parametrize("case", GN_CASES)
-def test_groupnorm_forward_backward(ops, ref, case):
+def test_groupnorm_forward_backward(ops, ref, case, rows_mb, monkeypatch):
+    """rows_mb = "0": the whole-row apply kernel that large (beyond-L2) tensors take, forced at these small sizes."""
+    if rows_mb is not None:
+        if case[7] != 0:
+            pytest.skip("the row kernel serves the un-resampled apply only")
+        monkeypatch.setenv("ISB_GN_ROWS_MIN_MB", rows_mb)
     N, H, W, C1, C2, film_on, silu, rs, want_raw = case
     g = G(3)
     C = C1 + C2
